@@ -1,0 +1,659 @@
+// C ABI of libspwombling: argument checking, device workspaces, host<->device marshalling of R-layout
+// arrays, and the per-shard driver of the spatial_gradient pipeline.  See include/spwombling.h.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/spwombling.h"
+#include "common.cuh"
+#include "cov.cuh"
+#include "gradient.cuh"
+#include "hlm.cuh"
+#include "linalg.cuh"
+#include "summary.cuh"
+
+namespace spw {
+
+static thread_local char tl_error[1024] = "";
+static char g_error[1024] = "";
+static std::mutex g_err_mu;
+long long g_launches = 0;
+static long long g_ws_limit = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  memcpy(g_error, tl_error, sizeof(g_error));
+}
+
+// ---- per-device context -----------------------------------------------------------------------------
+struct DeviceCtx {
+  cudaStream_t stream = nullptr;
+  std::map<std::pair<int, int>, LinalgPlan*> plans;
+  void* ws = nullptr;          // grow-only workspace
+  size_t ws_bytes = 0;
+};
+static DeviceCtx g_ctx[64];
+static std::mutex g_ctx_mu;
+
+static int get_ctx(DeviceCtx** out) {
+  int dev = 0;
+  SPW_CUDA(cudaGetDevice(&dev));
+  DeviceCtx& c = g_ctx[dev & 63];
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (!c.stream) SPW_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  *out = &c;
+  return SPW_OK;
+}
+
+static int get_plan(DeviceCtx& c, int n, int extra, const LinalgPlan** out) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto key = std::make_pair(n, extra);
+  auto it = c.plans.find(key);
+  if (it == c.plans.end()) {
+    LinalgPlan* p = new LinalgPlan();
+    int rc = plan_build(*p, n, extra);
+    if (rc != SPW_OK) {
+      delete p;
+      return rc;
+    }
+    it = c.plans.emplace(key, p).first;
+  }
+  *out = it->second;
+  return SPW_OK;
+}
+
+static int get_workspace(DeviceCtx& c, size_t bytes, void** out) {
+  if (bytes > c.ws_bytes) {
+    if (c.ws) SPW_CUDA(cudaFree(c.ws));
+    c.ws = nullptr;
+    c.ws_bytes = 0;
+    SPW_CUDA(cudaMalloc(&c.ws, bytes));
+    c.ws_bytes = bytes;
+  }
+  *out = c.ws;
+  return SPW_OK;
+}
+
+static size_t workspace_budget() {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return size_t(8) << 30;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  free_b += g_ctx[dev & 63].ws_bytes;   // our cached workspace is reusable
+  size_t budget = (size_t)(0.6 * (double)free_b);
+  if (g_ws_limit > 0 && (size_t)g_ws_limit < budget) budget = (size_t)g_ws_limit;
+  return budget;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base((char*)p) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) / 256 * 256;
+    T* r = (T*)(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+static int ncomp_of(int type) { return type == SPW_COV_MATERN1 ? 2 : 5; }
+static long long pad_ld(long long n) { return round_up_ll(n, 16); }
+
+// ---- the per-shard spatial_gradient driver (device pointers) -------------------------------------------
+static int gradient_shard(int type, int n, const double* cx, const double* cy, int G, const double* gx,
+                          const double* gy, int S, const double* phi, const double* sig2, const double* z, int ldz,
+                          const double* eps, double* out_draws, double* out_mean, double* out_var, int* info,
+                          cudaStream_t st) {
+  if (info) info[0] = info[1] = info[2] = info[3] = 0;
+  if (type < 0 || type > 2 || n < 1 || G < 1 || S < 0) { set_error("spw_gradient: bad arguments"); return SPW_ERR_ARG; }
+  if (out_draws && !eps) { set_error("spw_gradient: eps is required when draws are requested"); return SPW_ERR_ARG; }
+  if (S == 0) return SPW_OK;
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 0, &plan));
+  const int c = ncomp_of(type);
+  const long long ld = pad_ld(n);
+  const int nblk = plan->nblk;
+  // workspace sizing: batch B samples, grid chunk gc
+  const size_t mat = (size_t)n * ld * sizeof(double);
+  const size_t per_sample_fixed = 2 * mat + (size_t)ld * sizeof(double) + (size_t)nblk * NB * NB * sizeof(double) + 64;
+  const size_t at_per_g = (size_t)c * ld * sizeof(double);
+  const size_t budget = workspace_budget();
+  int gc = std::min(G, 65535);
+  int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / (per_sample_fixed + at_per_g * gc));
+  if (B < std::min(S, 16)) {   // not enough room for the whole grid at a useful batch size: chunk the grid
+    B = std::min(S, 16);
+    while (B > 1 && per_sample_fixed * B > budget / 2) B /= 2;
+    const size_t left = budget > per_sample_fixed * B ? budget - per_sample_fixed * B : 0;
+    gc = (int)std::min<size_t>((size_t)gc, left / (at_per_g * B));
+    gc = gc / 16 * 16;
+    if (gc < 16) { set_error("spw_gradient: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
+  }
+  const size_t total = (per_sample_fixed + at_per_g * gc) * B + 4096;
+  void* wsp;
+  SPW_TRY(get_workspace(*ctx, total, &wsp));
+  Carver cv(wsp);
+  double* Lb = cv.take<double>((size_t)B * n * ld);
+  double* Li = cv.take<double>((size_t)B * n * ld);
+  double* At = cv.take<double>((size_t)B * gc * c * ld);
+  double* vb = cv.take<double>((size_t)B * ld);
+  double* dinv = cv.take<double>((size_t)B * nblk * NB * NB);
+  int* status = cv.take<int>((size_t)2 * B);
+  std::vector<int> h_status(2 * (size_t)B);
+  MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld}, AT{At, ld, (long long)gc * c * ld};
+
+  for (int s0 = 0; s0 < S; s0 += B) {
+    const int nb = std::min(B, S - s0);
+    SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 2 * B, st));
+    // K = cov(phi_s, sig2 = 1), no nugget            R/spatial_gradient.R:215,264,303
+    SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, nullptr, 1, L, nb, 1, st));
+    // chol(K) and its triangular inverse            R/spatial_gradient.R:216,265,304
+    SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status, st));
+    SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    SPW_TRY(trmv_lower_batched(n, Linv, z + (long long)s0 * ldz, ldz, vb, ld, nb, st));
+    for (int g0 = 0; g0 < G; g0 += gc) {
+      const int ng = std::min(gc, G - g0);
+      SPW_TRY(cross_cov_batched(type, n, cx, cy, g0, ng, gx, gy, phi + s0, AT, nb, st));
+      GradParams P;
+      P.linv = Linv;
+      P.at = AT;
+      P.v = vb;
+      P.ldv = ld;
+      P.phi = phi + s0;
+      P.sig2 = sig2 + s0;
+      P.eps = eps;
+      P.out_draws = out_draws;
+      P.out_mean = out_mean;
+      P.out_var = out_var;
+      P.status = status + B;
+      P.n = n;
+      P.g_begin = g0;
+      P.g_count = ng;
+      P.g_total = G;
+      P.s_begin = s0;
+      SPW_TRY(gradient_main_launch(type, P, nb, st));
+    }
+    SPW_CUDA(cudaMemcpyAsync(h_status.data(), status, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < nb; ++b) {
+      if (h_status[b]) {
+        if (info) { info[0] = s0 + b + 1; info[1] = h_status[b]; info[2] = 1; }
+        set_error("spatial_gradient: sample %d: the leading minor of order %d of K is not positive", s0 + b + 1, h_status[b]);
+        return SPW_ERR_NOT_PD;
+      }
+      if (h_status[B + b]) {
+        if (info) { info[0] = s0 + b + 1; info[1] = h_status[B + b]; info[2] = 2; }
+        set_error("spatial_gradient: sample %d, grid point %d: var.grad is not positive definite", s0 + b + 1, h_status[B + b]);
+        return SPW_ERR_NOT_PD;
+      }
+    }
+  }
+  return SPW_OK;
+}
+
+// small RAII helper for temporary device buffers of the host-pointer entry points
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    SPW_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+    return SPW_OK;
+  }
+  template <class T> T* as() { return (T*)p; }
+};
+
+}  // namespace spw
+
+using namespace spw;
+
+extern "C" {
+
+int spw_version(void) { return 100; }
+
+const char* spw_last_error(void) {
+  if (tl_error[0]) return tl_error;
+  return g_error;
+}
+
+int spw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  return n;
+}
+
+int spw_set_device(int device) {
+  SPW_CUDA(cudaSetDevice(device));
+  return SPW_OK;
+}
+
+int spw_set_workspace_limit(long long bytes) {
+  g_ws_limit = bytes;
+  return SPW_OK;
+}
+
+long long spw_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int spw_shutdown(void) {
+  int cur = 0, ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) return SPW_OK;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < ndev && d < 64; ++d) {
+    DeviceCtx& c = g_ctx[d];
+    if (!c.stream && !c.ws && c.plans.empty()) continue;
+    cudaSetDevice(d);
+    for (auto& kv : c.plans) {
+      plan_free(*kv.second);
+      delete kv.second;
+    }
+    c.plans.clear();
+    if (c.ws) cudaFree(c.ws);
+    c.ws = nullptr;
+    c.ws_bytes = 0;
+    if (c.stream) cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+  }
+  cudaSetDevice(cur);
+  return SPW_OK;
+}
+
+int spw_cov(int type, int n, const double* coords, double phi, double sig2, double* out) {
+  if (type < 0 || type > 2 || n < 1 || !coords || !out) { set_error("spw_cov: bad arguments"); return SPW_ERR_ARG; }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const long long ld = pad_ld(n);
+  DevBuf dc, dp, dm;
+  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
+  SPW_TRY(dp.alloc(sizeof(double) * 2));
+  SPW_TRY(dm.alloc(sizeof(double) * n * ld));
+  const double par[2] = {phi, sig2};
+  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dp.p, par, sizeof(par), cudaMemcpyHostToDevice, st));
+  MatView M{dm.as<double>(), ld, (long long)n * ld};
+  SPW_TRY(cov_assemble_batched(type, n, dc.as<double>(), dc.as<double>() + n, dp.as<double>(), dp.as<double>() + 1,
+                               nullptr, 0, M, 1, 0, st));
+  SPW_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * n, dm.p, sizeof(double) * ld, sizeof(double) * n, n,
+                             cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
+int spw_cov_delta(int type, long long len, const double* delta, double phi, double sig2, double* out) {
+  if (type < 0 || type > 2 || len < 0 || (len && (!delta || !out))) { set_error("spw_cov_delta: bad arguments"); return SPW_ERR_ARG; }
+  if (len == 0) return SPW_OK;
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  DevBuf din, dout;
+  SPW_TRY(din.alloc(sizeof(double) * len));
+  SPW_TRY(dout.alloc(sizeof(double) * len));
+  SPW_CUDA(cudaMemcpyAsync(din.p, delta, sizeof(double) * len, cudaMemcpyHostToDevice, st));
+  SPW_TRY(cov_delta(type, len, din.as<double>(), phi, sig2, dout.as<double>(), st));
+  SPW_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * len, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
+int spw_cross_cov(int type, int n, const double* coords, int g, const double* grid, double phi, double* out) {
+  if (type < 0 || type > 2 || n < 1 || g < 1 || !coords || !grid || !out) { set_error("spw_cross_cov: bad arguments"); return SPW_ERR_ARG; }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const int c = ncomp_of(type);
+  const long long ld = pad_ld(n);
+  DevBuf dc, dg, dp, da;
+  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
+  SPW_TRY(dg.alloc(sizeof(double) * 2 * g));
+  SPW_TRY(dp.alloc(sizeof(double)));
+  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dg.p, grid, sizeof(double) * 2 * g, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dp.p, &phi, sizeof(double), cudaMemcpyHostToDevice, st));
+  const int gc = std::min(g, 8192);
+  SPW_TRY(da.alloc(sizeof(double) * (size_t)gc * c * ld));
+  MatView AT{da.as<double>(), ld, (long long)gc * c * ld};
+  for (int g0 = 0; g0 < g; g0 += gc) {
+    const int ng = std::min(gc, g - g0);
+    SPW_TRY(cross_cov_batched(type, n, dc.as<double>(), dc.as<double>() + n, g0, ng, dg.as<double>(),
+                              dg.as<double>() + g, dp.as<double>(), AT, 1, st));
+    SPW_CUDA(cudaMemcpy2DAsync(out + (size_t)g0 * c * n, sizeof(double) * n, da.p, sizeof(double) * ld,
+                               sizeof(double) * n, (size_t)ng * c, cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaStreamSynchronize(st));
+  }
+  return SPW_OK;
+}
+
+int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) {
+  if (n < 1 || !a || !u) { set_error("spw_chol: bad arguments"); return SPW_ERR_ARG; }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 0, &plan));
+  const long long ld = pad_ld(n);
+  DevBuf dm, dd, ds, dl;
+  SPW_TRY(dm.alloc(sizeof(double) * n * ld));
+  SPW_TRY(dd.alloc(sizeof(double) * plan->nblk * NB * NB));
+  SPW_TRY(ds.alloc(sizeof(int)));
+  SPW_TRY(dl.alloc(sizeof(double)));
+  SPW_CUDA(cudaMemsetAsync(ds.p, 0, sizeof(int), st));
+  // R's column-major upper triangle a[i + n*j] (i <= j) is this library's row-major lower triangle L[j][i]
+  SPW_CUDA(cudaMemcpy2DAsync(dm.p, sizeof(double) * ld, a, sizeof(double) * n, sizeof(double) * n, n,
+                             cudaMemcpyHostToDevice, st));
+  MatView L{dm.as<double>(), ld, (long long)n * ld};
+  SPW_TRY(potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st));
+  SPW_TRY(logdet_quad_batched(n, L, dl.as<double>(), nullptr, 1, st));
+  std::vector<double> tmp((size_t)n * n);
+  int status = 0;
+  double ld_half = 0.0;
+  SPW_CUDA(cudaMemcpy2DAsync(tmp.data(), sizeof(double) * n, dm.p, sizeof(double) * ld, sizeof(double) * n, n,
+                             cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaMemcpyAsync(&status, ds.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaMemcpyAsync(&ld_half, dl.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  if (info) *info = status;
+  if (status) {
+    set_error("the leading minor of order %d is not positive", status);
+    return SPW_ERR_NOT_PD;
+  }
+  for (int j = 0; j < n; ++j)        // column j of U: rows i <= j hold L[j][i]; zeros below the diagonal
+    for (int i = 0; i < n; ++i) u[i + (size_t)n * j] = (i <= j) ? tmp[(size_t)j * n + i] : 0.0;
+  if (logdet_half) *logdet_half = ld_half;
+  return SPW_OK;
+}
+
+int spw_hlm_run(int n, const double* coords, const double* y, int type, int niter, int nburn, int report,
+                double a_sigma, double b_sigma, double a_tau, double b_tau, double lower_phi, double upper_phi,
+                const double* norm, const double* unif, int want_trgt, double* out_sig2, double* out_tau2,
+                double* out_phi, double* out_trgt, double* out_accept, double* out_tuning, int* info) {
+  (void)nburn;   // the R host slices (nburn+1):niter; the full chains are returned
+  if (type < 0 || type > 2 || n < 1 || niter < 0 || report < 1 || !coords || !y || !norm || !unif || !out_sig2 ||
+      !out_tau2 || !out_phi || (want_trgt && !out_trgt)) {
+    set_error("spw_hlm_run: bad arguments");
+    return SPW_ERR_ARG;
+  }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 1, &plan));
+  const long long ld = pad_ld(n);
+  const int nrep = niter / report;
+  DevBuf dc, dy, dnorm, dunif, dL, dd, ds, dstate, dout;
+  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
+  SPW_TRY(dy.alloc(sizeof(double) * n));
+  SPW_TRY(dnorm.alloc(sizeof(double) * 3 * (size_t)std::max(niter, 1)));
+  SPW_TRY(dunif.alloc(sizeof(double) * 3 * (size_t)std::max(niter, 1)));
+  SPW_TRY(dL.alloc(sizeof(double) * (size_t)(n + 1) * ld));
+  SPW_TRY(dd.alloc(sizeof(double) * plan->nblk * NB * NB));
+  SPW_TRY(ds.alloc(sizeof(int)));
+  SPW_TRY(dstate.alloc(hlm_state_bytes()));
+  const size_t n_out = 3 * (size_t)niter + (size_t)niter + 1 + 6 * (size_t)std::max(nrep, 1);
+  SPW_TRY(dout.alloc(sizeof(double) * n_out));
+  SPW_CUDA(cudaMemsetAsync(dout.p, 0, sizeof(double) * n_out, st));
+  double* o_sig2 = dout.as<double>();
+  double* o_tau2 = o_sig2 + niter;
+  double* o_phi = o_tau2 + niter;
+  double* o_trgt = o_phi + niter;
+  double* o_acc = o_trgt + niter + 1;
+  double* o_tun = o_acc + 3 * (size_t)std::max(nrep, 1);
+  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dy.p, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (niter > 0) {
+    SPW_CUDA(cudaMemcpyAsync(dnorm.p, norm, sizeof(double) * 3 * (size_t)niter, cudaMemcpyHostToDevice, st));
+    SPW_CUDA(cudaMemcpyAsync(dunif.p, unif, sizeof(double) * 3 * (size_t)niter, cudaMemcpyHostToDevice, st));
+  }
+  HlmWorkspace ws;
+  ws.L = dL.as<double>();
+  ws.ld = ld;
+  ws.dinv = dd.as<double>();
+  ws.status = ds.as<int>();
+  ws.state = (HlmState*)dstate.p;
+  ws.plan = plan;
+  int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
+                       b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
+                       o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);
+  if (rc != SPW_OK && rc != SPW_ERR_NOT_PD) return rc;
+  if (niter > 0) {
+    SPW_CUDA(cudaMemcpyAsync(out_sig2, o_sig2, sizeof(double) * niter, cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaMemcpyAsync(out_tau2, o_tau2, sizeof(double) * niter, cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaMemcpyAsync(out_phi, o_phi, sizeof(double) * niter, cudaMemcpyDeviceToHost, st));
+  }
+  if (want_trgt) SPW_CUDA(cudaMemcpyAsync(out_trgt, o_trgt, sizeof(double) * ((size_t)niter + 1), cudaMemcpyDeviceToHost, st));
+  if (nrep > 0 && out_accept) SPW_CUDA(cudaMemcpyAsync(out_accept, o_acc, sizeof(double) * 3 * nrep, cudaMemcpyDeviceToHost, st));
+  if (nrep > 0 && out_tuning) SPW_CUDA(cudaMemcpyAsync(out_tuning, o_tun, sizeof(double) * 3 * nrep, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int spw_gradient_shard_dev(int type, int n, const double* coords_dev, int g, const double* grid_dev, int S,
+                           const double* phi_dev, const double* sig2_dev, const double* z_dev, int ldz,
+                           const double* eps_dev, double* out_draws_dev, double* out_mean_dev, double* out_var_dev,
+                           int* info, void* stream) {
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return gradient_shard(type, n, coords_dev, coords_dev + n, g, grid_dev, grid_dev + g, S, phi_dev, sig2_dev, z_dev,
+                        ldz, eps_dev, out_draws_dev, out_mean_dev, out_var_dev, info, st);
+}
+
+// one device's share of spw_gradient_run: samples [s_lo, s_hi).  The shard's draws stay on the device
+// (layout [Sl][c][g]) for the gather; moments go straight back to the host.
+struct ShardResult {
+  DevBuf draws;      // [Sl][c][g] on the shard's device (unless written in place into the gather buffer)
+};
+
+static int gradient_run_one(int device, int type, int n, const double* coords, int g, const double* grid, int S,
+                            int s_lo, int s_hi, const double* phi, const double* sig2, const double* z,
+                            const double* eps, bool want_draws, double* draws_inplace, ShardResult* res,
+                            double* out_mean, double* out_var, int* info) {
+  SPW_CUDA(cudaSetDevice(device));
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const int c = ncomp_of(type), Sl = s_hi - s_lo;
+  if (Sl <= 0) return SPW_OK;
+  const long long ldz = pad_ld(n);
+  DevBuf dc, dg, dphi, dsig, dzr, dz, deps, dmean, dvar;
+  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
+  SPW_TRY(dg.alloc(sizeof(double) * 2 * g));
+  SPW_TRY(dphi.alloc(sizeof(double) * Sl));
+  SPW_TRY(dsig.alloc(sizeof(double) * Sl));
+  SPW_TRY(dzr.alloc(sizeof(double) * (size_t)Sl * n));
+  SPW_TRY(dz.alloc(sizeof(double) * (size_t)Sl * ldz));
+  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dg.p, grid, sizeof(double) * 2 * g, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dphi.p, phi + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dsig.p, sig2 + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
+  // model$z is S x n column-major: bring rows s_lo..s_hi of every column, then transpose to [Sl][ldz]
+  SPW_CUDA(cudaMemcpy2DAsync(dzr.p, sizeof(double) * Sl, z + s_lo, sizeof(double) * S, sizeof(double) * Sl, n,
+                             cudaMemcpyHostToDevice, st));
+  SPW_TRY(transpose_batched(n, Sl, dzr.as<double>(), Sl, 0, dz.as<double>(), ldz, 0, 1, st));
+  double* ddraw = nullptr;
+  if (want_draws) {
+    SPW_TRY(deps.alloc(sizeof(double) * (size_t)Sl * g * c));
+    SPW_CUDA(cudaMemcpyAsync(deps.p, eps + (size_t)s_lo * g * c, sizeof(double) * (size_t)Sl * g * c,
+                             cudaMemcpyHostToDevice, st));
+    if (draws_inplace) {
+      ddraw = draws_inplace;
+    } else {
+      SPW_TRY(res->draws.alloc(sizeof(double) * (size_t)Sl * g * c));
+      ddraw = res->draws.as<double>();
+    }
+  }
+  if (out_mean) SPW_TRY(dmean.alloc(sizeof(double) * (size_t)Sl * g * c));
+  if (out_var) SPW_TRY(dvar.alloc(sizeof(double) * (size_t)Sl * g * c * c));
+  int rc = gradient_shard(type, n, dc.as<double>(), dc.as<double>() + n, g, dg.as<double>(), dg.as<double>() + g, Sl,
+                          dphi.as<double>(), dsig.as<double>(), dz.as<double>(), (int)ldz,
+                          want_draws ? deps.as<double>() : nullptr, ddraw,
+                          out_mean ? dmean.as<double>() : nullptr, out_var ? dvar.as<double>() : nullptr, info, st);
+  if (rc != SPW_OK) {
+    if (info && info[0] > 0) info[0] += s_lo;
+    return rc;
+  }
+  if (out_mean)
+    SPW_CUDA(cudaMemcpyAsync(out_mean + (size_t)s_lo * g * c, dmean.p, sizeof(double) * (size_t)Sl * g * c,
+                             cudaMemcpyDeviceToHost, st));
+  if (out_var)
+    SPW_CUDA(cudaMemcpyAsync(out_var + (size_t)s_lo * g * c * c, dvar.p, sizeof(double) * (size_t)Sl * g * c * c,
+                             cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
+int spw_gradient_run(int type, int n, const double* coords, int g, const double* grid, int S, const double* phi,
+                     const double* sig2, const double* z, const double* eps, int ngpu, int nbatch, double prob,
+                     double* out_draws, double* out_summary, double* out_mean, double* out_var, int* info) {
+  if (type < 0 || type > 2 || n < 1 || g < 1 || S < 0 || !coords || !grid || (S && (!phi || !sig2 || !z))) {
+    set_error("spw_gradient_run: bad arguments");
+    return SPW_ERR_ARG;
+  }
+  const bool want_draws = out_draws || out_summary;
+  if (want_draws && !eps) { set_error("spw_gradient_run: eps is required when draws are requested"); return SPW_ERR_ARG; }
+  if (out_summary && nbatch < 1) { set_error("spw_gradient_run: nbatch must be >= 1 for the summary"); return SPW_ERR_ARG; }
+  if (info) info[0] = info[1] = info[2] = info[3] = 0;
+  if (S == 0) return SPW_OK;
+  int ndev = spw_device_count();
+  if (ndev < 1) { set_error("spw_gradient_run: no CUDA device"); return SPW_ERR_CUDA; }
+  if (ngpu < 1) ngpu = 1;
+  if (ngpu > ndev) { set_error("spw_gradient_run: ngpu = %d but only %d devices", ngpu, ndev); return SPW_ERR_ARG; }
+  if (ngpu > S) ngpu = S;
+  int root = 0;
+  SPW_CUDA(cudaGetDevice(&root));
+  if (ngpu > 1) root = 0;
+  const int c = ncomp_of(type);
+  // gather buffer on the root device: all draws, sample-major [S][c][g]
+  SPW_CUDA(cudaSetDevice(root));
+  DeviceCtx* rctx;
+  SPW_TRY(get_ctx(&rctx));
+  cudaStream_t rst = rctx->stream;
+  DevBuf dall, dr, dsum;
+  if (want_draws) SPW_TRY(dall.alloc(sizeof(double) * (size_t)S * g * c));
+  auto lo_of = [&](int d) { return (int)((long long)S * d / ngpu); };
+  // contiguous sample shards, one host thread per device (R/spatial_gradient.R:29-32,200)
+  std::vector<int> rcs(ngpu, SPW_OK);
+  std::vector<std::vector<int>> infos(ngpu, std::vector<int>(4, 0));
+  std::vector<std::string> errs(ngpu);
+  std::vector<ShardResult> results(ngpu);
+  auto work = [&](int d) {
+    const int dev = (ngpu > 1) ? d : root;
+    double* inplace = (want_draws && dev == root) ? dall.as<double>() + (size_t)lo_of(d) * g * c : nullptr;
+    rcs[d] = gradient_run_one(dev, type, n, coords, g, grid, S, lo_of(d), lo_of(d + 1), phi, sig2, z, eps, want_draws,
+                              inplace, &results[d], out_mean, out_var, infos[d].data());
+    if (rcs[d] != SPW_OK) errs[d] = tl_error;
+  };
+  if (ngpu == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ngpu; ++d) th.emplace_back(work, d);
+    for (auto& t : th) t.join();
+  }
+  SPW_CUDA(cudaSetDevice(root));
+  auto free_shards = [&]() {   // shard buffers live on their own devices
+    for (int d = 0; d < ngpu; ++d) {
+      if (!results[d].draws.p) continue;
+      cudaSetDevice((ngpu > 1) ? d : root);
+      cudaFree(results[d].draws.p);
+      results[d].draws.p = nullptr;
+    }
+    cudaSetDevice(root);
+  };
+  for (int d = 0; d < ngpu; ++d)
+    if (rcs[d] != SPW_OK) {
+      if (info) memcpy(info, infos[d].data(), sizeof(int) * 4);
+      set_error("%s", errs[d].c_str());
+      free_shards();
+      return rcs[d];
+    }
+  if (!want_draws) return SPW_OK;
+  // the one gather: peer copies of the shards into the root's buffer (R/spatial_gradient.R:378-390 rbind)
+  for (int d = 0; d < ngpu; ++d) {
+    const int dev = (ngpu > 1) ? d : root;
+    if (dev == root) continue;
+    const size_t cnt = (size_t)(lo_of(d + 1) - lo_of(d)) * g * c;
+    SPW_CUDA(cudaMemcpyPeerAsync(dall.as<double>() + (size_t)lo_of(d) * g * c, root, results[d].draws.p, dev,
+                                 sizeof(double) * cnt, rst));
+  }
+  if (out_summary) {
+    SPW_TRY(dsum.alloc(sizeof(double) * 3 * (size_t)g * c));
+    SPW_TRY(hpd_summary_dev(S, g, c, nbatch, prob, dall.as<double>(), dsum.as<double>(), rst));
+    SPW_CUDA(cudaMemcpyAsync(out_summary, dsum.p, sizeof(double) * 3 * (size_t)g * c, cudaMemcpyDeviceToHost, rst));
+  }
+  if (out_draws) {
+    // [S][c][g] -> the c matrices S x g, column-major: out_draws[s + S*(j + g*a)]
+    SPW_TRY(dr.alloc(sizeof(double) * (size_t)S * g * c));
+    SPW_TRY(transpose_batched(S, c * g, dall.as<double>(), (long long)c * g, 0, dr.as<double>(), S, 0, 1, rst));
+    SPW_CUDA(cudaMemcpyAsync(out_draws, dr.p, sizeof(double) * (size_t)S * g * c, cudaMemcpyDeviceToHost, rst));
+  }
+  SPW_CUDA(cudaStreamSynchronize(rst));
+  free_shards();
+  return SPW_OK;
+}
+
+int spw_hpd_summary_dev(int S, int g, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
+                        void* stream) {
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return hpd_summary_dev(S, g, ncomp, nbatch, prob, draws_dev, out_dev, st);
+}
+
+int spw_draws_to_r_layout_dev(int S, int g, int ncomp, const double* draws_dev, double* out_dev, void* stream) {
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return transpose_batched(S, ncomp * g, draws_dev, (long long)ncomp * g, 0, out_dev, S, 0, 1, st);
+}
+
+int spw_hpd_summary(int S, int g, int nbatch, double prob, const double* draws, double* out) {
+  if (S < 1 || g < 1 || !draws || !out) { set_error("spw_hpd_summary: bad arguments"); return SPW_ERR_ARG; }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  DevBuf din, dt, dout;
+  SPW_TRY(din.alloc(sizeof(double) * (size_t)S * g));
+  SPW_TRY(dt.alloc(sizeof(double) * (size_t)S * g));
+  SPW_TRY(dout.alloc(sizeof(double) * 3 * (size_t)g));
+  SPW_CUDA(cudaMemcpyAsync(din.p, draws, sizeof(double) * (size_t)S * g, cudaMemcpyHostToDevice, st));
+  // R layout [g][S] (S contiguous) -> [S][1][g]
+  SPW_TRY(transpose_batched(g, S, din.as<double>(), S, 0, dt.as<double>(), g, 0, 1, st));
+  SPW_TRY(hpd_summary_dev(S, g, 1, nbatch, prob, dt.as<double>(), dout.as<double>(), st));
+  SPW_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * 3 * (size_t)g, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
+int spw_cov_p(const int* type, const int* n, const double* coords, const double* phi, const double* sig2, double* out,
+              int* status) {
+  const int rc = spw_cov(*type, *n, coords, *phi, *sig2, out);
+  if (status) *status = rc;
+  return rc;
+}
+
+int spw_hpd_summary_p(const int* S, const int* g, const int* nbatch, const double* prob, const double* draws,
+                      double* out, int* status) {
+  const int rc = spw_hpd_summary(*S, *g, *nbatch, *prob, draws, out);
+  if (status) *status = rc;
+  return rc;
+}
+
+}  // extern "C"

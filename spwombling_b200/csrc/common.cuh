@@ -1,0 +1,84 @@
+// Shared device helpers for libspwombling (sm_100a, fp64).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace spw {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern long long g_launches;   // kernels launched by this library (spw_launch_count)
+
+#define SPW_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      spw::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SPW_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define SPW_LAUNCHED()                                                                        \
+  do {                                                                                        \
+    ++spw::g_launches;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                 \
+      spw::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SPW_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define SPW_TRY(call)                    \
+  do {                                   \
+    int rc__ = (call);                   \
+    if (rc__ != SPW_OK) return rc__;     \
+  } while (0)
+
+// ---- FP64 tensor pipe: mma.sync m8n8k4 (SASS DMMA.8x8x4) ---------------------------------------
+// fragment ownership (lane = 4*g + q, g = lane>>2, q = lane&3):
+//   A (8x4, row):  a  = A[g][q]
+//   B (4x8, col):  b  = B[q][g]
+//   C (8x8):       c0 = C[g][2q], c1 = C[g][2q+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- cp.async (LDGSTS), 16-byte, L2-only (.cg) with zero-fill of the bytes past src_bytes -------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---- covariance functions of the reference (R/cov_gaussian.R:14, R/cov_matern1.R:14, R/cov_matern2.R:14)
+// rho(d) with sig2 = 1; the gaussian kernel squares the (square-rooted) distance as the reference does.
+template <int TYPE>
+__device__ __forceinline__ double cov_rho(double phi, double d) {
+  if constexpr (TYPE == 0) {
+    return exp(-phi * (d * d));
+  } else if constexpr (TYPE == 1) {
+    const double ad = phi * 1.7320508075688772 * d;   // phi * sqrt(3) * Delta
+    return (1.0 + ad) * exp(-ad);
+  } else {
+    const double ad = phi * 2.2360679774997898 * d;   // phi * sqrt(5) * Delta
+    return (1.0 + ad + phi * phi * 5.0 * (d * d) / 3.0) * exp(-ad);
+  }
+}
+
+}  // namespace spw

@@ -1,0 +1,28 @@
+// hlmBayes_sp device chain (see hlm.cu).
+#pragma once
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace spw {
+
+struct HlmState;
+
+struct HlmWorkspace {
+  double* L = nullptr;        // (n + 1) x ld work matrix: Sigma' lower triangle, row n = y^T
+  long long ld = 0;
+  double* dinv = nullptr;     // inverted diagonal blocks
+  int* status = nullptr;
+  HlmState* state = nullptr;
+  const LinalgPlan* plan = nullptr;   // built with extra_rows = 1
+};
+
+size_t hlm_state_bytes();
+
+// All pointers are device pointers except info_host.  Outputs as documented for spw_hlm_run.
+int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const double* cy, const double* y_dev,
+                int niter, int report, double a_sigma, double b_sigma, double a_tau, double b_tau,
+                double lower_phi, double upper_phi, const double* norm_dev, const double* unif_dev, int want_trgt,
+                double* out_sig2, double* out_tau2, double* out_phi, double* out_trgt, double* out_accept,
+                double* out_tuning, int* info_host, cudaStream_t st);
+
+}  // namespace spw

@@ -1,0 +1,66 @@
+// Batched blocked fp64 dense linear algebra on row-major lower-triangular storage
+// (bit-identical to R's column-major upper factor chol(): L[i][j] row-major == U[j, i] column-major).
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "../../include/spwombling.h"
+
+namespace spw {
+
+constexpr int NB = 64;   // diagonal block size of the blocked Cholesky / triangular inverse
+
+// One output tile of the task-driven NT GEMM kernel.
+struct GemmTask {
+  int a_row, a_col;     // origin of the A block; k runs along columns a_col .. a_col + k
+  int b_row, b_col;     // origin of the B block (rows = n index)
+  int c_row, c_col;     // origin of the C tile
+  int ct_row, ct_col;   // origin of the transposed store (row = n index, col = m index)
+  int m, n, k;          // extents
+  int a_tri, a_lim0, b_tri, b_lim0;   // see gemm_nt.cuh TriMask
+  int flags;            // GT_*
+};
+enum : int { GT_ACCUM = 1, GT_STORE = 2, GT_STORE_T = 4 };
+
+struct MatView {        // a batch of row-major matrices
+  double* p;
+  long long ld;         // doubles
+  long long stride;     // doubles between consecutive batch entries
+};
+
+// Schedule for one matrix order n: per-step slices into one device-resident task array.
+struct ChunkRange { int begin, count; };
+struct LinalgPlan {
+  int n = 0;            // matrix order the plan was built for
+  int rows = 0;         // rows actually factored (n, or n + 1 for the augmented hlm system)
+  int nblk = 0;
+  std::vector<ChunkRange> panel, trail;         // per potrf step
+  std::vector<ChunkRange> inv1, inv2;           // per trtri level
+  GemmTask* d_tasks = nullptr;
+  int n_tasks = 0;
+};
+
+int plan_build(LinalgPlan& plan, int n, int extra_rows);
+void plan_free(LinalgPlan& plan);
+
+// Batched Cholesky of the leading n x n lower triangle of L (in place).  If extra_rows > 0 the rows
+// n .. n+extra_rows-1 (full-length rows appended below the matrix) are carried through the panel
+// solves: on exit row n holds (L^-1 y)^T when it held y^T on entry.  dinv: [batch][nblk][NB*NB] scratch
+// for the inverted diagonal blocks.  linv (optional): receives the inverted diagonal blocks (lower part
+// and mirrored upper part) as the level-0 state of the triangular inverse.
+// status[b] is set to the (1-based) order of the first non-positive leading minor, 0 if none.
+int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv, int batch, int* status,
+                  cudaStream_t st);
+
+// Batched inverse of the lower-triangular factor: on exit the lower triangle of linv holds L^-1 and the
+// upper triangle its transpose.  Uses the strict upper triangle of L as scratch.  Requires the
+// level-0 state written by potrf_batched.
+int trtri_batched(const LinalgPlan& plan, MatView L, MatView linv, int batch, cudaStream_t st);
+
+// v[b][i] = sum_{k<=i} T[b][i][k] * x[b][k]   (lower-triangular matrix-vector product)
+int trmv_lower_batched(int n, MatView T, const double* x, long long ldx, double* v, long long ldv, int batch,
+                       cudaStream_t st);
+
+// sum_i log(L[i][i]) and sum_k row[k]^2 per batch entry (hlm log-determinant and quadratic form)
+int logdet_quad_batched(int n, MatView L, double* logdet_half, double* quad, int batch, cudaStream_t st);
+
+}  // namespace spw

@@ -1,0 +1,151 @@
+// Batch medians, median of batch medians and HPD interval of the gradient draws; layout transposes.
+//   ngrad / slist / batch medians / estimates / HPDinterval   R/spatial_gradient.R:391-419 (:353-358 matern1)
+//   coda::HPDinterval.mcmc (coda 0.19): sort; gap = max(1, min(n-1, round(n*prob))); first minimal-width window.
+// All kernels put consecutive grid points on consecutive threads (coalesced over the [S][ncomp][G] layout) and
+// select order statistics by rank counting (ties broken by index), which is exact and order-independent.
+#include <cmath>
+#include <vector>
+#include "summary.cuh"
+
+namespace spw {
+
+// one thread per (batch, comp, grid point): median of draws[s][comp][g], s in [bstart[b], bstart[b+1])
+__global__ void __launch_bounds__(128)
+batch_median_kernel(int G, int ncomp, int nb, const int* __restrict__ bstart, const double* __restrict__ draws,
+                    double* __restrict__ med /* [ncomp][nb][G] */) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y, a = blockIdx.z;
+  if (g >= G) return;
+  const int s0 = bstart[b], L = bstart[b + 1] - s0;
+  const long long stride = (long long)ncomp * G;
+  const double* x = draws + ((long long)s0 * ncomp + a) * G + g;
+  const int lo = (L - 1) / 2, hi = L / 2;
+  double vlo = 0.0, vhi = 0.0;
+  for (int i = 0; i < L; ++i) {
+    const double xi = x[i * stride];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const double xj = x[j * stride];
+      rank += (xj < xi) || (xj == xi && j < i);
+    }
+    if (rank == lo) vlo = xi;
+    if (rank == hi) vhi = xi;
+  }
+  med[((long long)a * nb + b) * G + g] = (lo == hi) ? vlo : (vlo + vhi) / 2.0;   // R median: mean of the two middle values
+}
+
+// one thread per (comp, grid point): sort the nb batch medians, estimate = their median, HPD window
+__global__ void __launch_bounds__(128)
+hpd_kernel(int G, int nb, int gap, const double* __restrict__ med, double* __restrict__ sorted,
+           double* __restrict__ out /* [ncomp][3][G] */) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  if (g >= G) return;
+  const double* x = med + (long long)a * nb * G + g;
+  double* srt = sorted + (long long)a * nb * G + g;
+  for (int i = 0; i < nb; ++i) {
+    const double xi = x[(long long)i * G];
+    int rank = 0;
+    for (int j = 0; j < nb; ++j) {
+      const double xj = x[(long long)j * G];
+      rank += (xj < xi) || (xj == xi && j < i);
+    }
+    srt[(long long)rank * G] = xi;
+  }
+  const int lo = (nb - 1) / 2, hi = nb / 2;
+  const double est = (lo == hi) ? srt[(long long)lo * G] : (srt[(long long)lo * G] + srt[(long long)hi * G]) / 2.0;
+  int best = 0;
+  double bw = srt[(long long)gap * G] - srt[0];
+  for (int i = 1; i + gap < nb; ++i) {
+    const double w = srt[(long long)(i + gap) * G] - srt[(long long)i * G];
+    if (w < bw) {   // strict: first minimum, like which.min
+      bw = w;
+      best = i;
+    }
+  }
+  double* o = out + (long long)a * 3 * G + g;
+  o[0] = est;
+  o[G] = srt[(long long)best * G];
+  o[2 * (long long)G] = srt[(long long)(best + gap) * G];
+}
+
+// tiled transpose of a batch of row-major [rows][cols] matrices -> [cols][rows]
+__global__ void __launch_bounds__(256)
+transpose_kernel(int rows, int cols, const double* __restrict__ in, long long in_ld, long long in_bstride,
+                 double* __restrict__ out, long long out_ld, long long out_bstride) {
+  __shared__ double tile[32][33];
+  const int bz = blockIdx.z;
+  const double* ip = in + (long long)bz * in_bstride;
+  double* op = out + (long long)bz * out_bstride;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = ip[(long long)r * in_ld + c];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) op[(long long)c * out_ld + r] = tile[tx][i];
+  }
+}
+
+int transpose_batched(int rows, int cols, const double* in, long long in_ld, long long in_bstride, double* out,
+                      long long out_ld, long long out_bstride, int batch, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return SPW_OK;
+  const int gx = ceil_div(cols, 32), gy_total = ceil_div(rows, 32);
+  for (int y0 = 0; y0 < gy_total; y0 += 65535) {
+    const int gy = std::min(65535, gy_total - y0);
+    transpose_kernel<<<dim3(gx, gy, batch), 256, 0, st>>>(rows - y0 * 32, cols, in + (long long)y0 * 32 * in_ld, in_ld,
+                                                          in_bstride, out + (long long)y0 * 32, out_ld, out_bstride);
+    SPW_LAUNCHED();
+  }
+  return SPW_OK;
+}
+
+std::vector<int> batch_starts(int S, int nbatch) {
+  // split(ngrad, ceiling(seq_along(ngrad) / (length(ngrad)/nbatch)))  -- R/spatial_gradient.R:392, in double arithmetic
+  std::vector<int> starts;
+  const double per = (double)S / (double)nbatch;
+  double prev = -1.0;
+  for (int j = 1; j <= S; ++j) {
+    const double lab = std::ceil((double)j / per);
+    if (lab != prev) {
+      starts.push_back(j - 1);
+      prev = lab;
+    }
+  }
+  starts.push_back(S);
+  return starts;
+}
+
+int hpd_gap(int nb, double prob) {
+  const int r = (int)std::nearbyint((double)nb * prob);   // R round(): half to even
+  return std::max(1, std::min(nb - 1, r));
+}
+
+int hpd_summary_dev(int S, int G, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
+                    cudaStream_t st) {
+  if (S < 1 || G < 1 || nbatch < 1) { set_error("hpd_summary: bad sizes"); return SPW_ERR_ARG; }
+  std::vector<int> starts = batch_starts(S, nbatch);
+  const int nb = (int)starts.size() - 1;
+  if (nb < 2) { set_error("hpd_summary: obj must have nsamp > 1 (need at least two batches)"); return SPW_ERR_ARG; }
+  if (nb > 65535) { set_error("hpd_summary: too many batches"); return SPW_ERR_ARG; }
+  int* d_starts = nullptr;
+  double *d_med = nullptr, *d_sorted = nullptr;
+  SPW_CUDA(cudaMallocAsync(&d_starts, sizeof(int) * starts.size(), st));
+  SPW_CUDA(cudaMallocAsync(&d_med, sizeof(double) * (size_t)ncomp * nb * G, st));
+  SPW_CUDA(cudaMallocAsync(&d_sorted, sizeof(double) * (size_t)ncomp * nb * G, st));
+  SPW_CUDA(cudaMemcpyAsync(d_starts, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice, st));
+  batch_median_kernel<<<dim3(ceil_div(G, 128), nb, ncomp), 128, 0, st>>>(G, ncomp, nb, d_starts, draws_dev, d_med);
+  SPW_LAUNCHED();
+  hpd_kernel<<<dim3(ceil_div(G, 128), ncomp), 128, 0, st>>>(G, nb, hpd_gap(nb, prob), d_med, d_sorted, out_dev);
+  SPW_LAUNCHED();
+  SPW_CUDA(cudaStreamSynchronize(st));   // starts vector must outlive the async copy
+  SPW_CUDA(cudaFreeAsync(d_starts, st));
+  SPW_CUDA(cudaFreeAsync(d_med, st));
+  SPW_CUDA(cudaFreeAsync(d_sorted, st));
+  return SPW_OK;
+}
+
+}  // namespace spw

@@ -1,0 +1,21 @@
+// Summary / layout kernels (see summary.cu).
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+#include "../../include/spwombling.h"
+
+namespace spw {
+
+std::vector<int> batch_starts(int S, int nbatch);
+int hpd_gap(int nb, double prob);
+
+// draws_dev [S][ncomp][G] -> out_dev [ncomp][3][G] (estimate, lower, upper)
+int hpd_summary_dev(int S, int G, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
+                    cudaStream_t st);
+
+// batch of row-major [rows][cols] -> [cols][rows]
+int transpose_batched(int rows, int cols, const double* in, long long in_ld, long long in_bstride, double* out,
+                      long long out_ld, long long out_bstride, int batch, cudaStream_t st);
+
+}  // namespace spw
