@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the spatial_gradient hot path (BASELINE.json metric: posterior-sample x grid-point / s).
+
+    python bench.py --gpus N --steps K --warmup W            # one process per GPU (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the restated reference algorithm on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic posterior samples (per rank; weak scaling):
+covariance assembly -> batched Cholesky -> triangular inverse -> cross-covariances -> fused TRMM + Gram +
+5x5 Cholesky + draw for every grid point, plus (N > 1) the single NCCL gather of the draws to rank 0.
+`value` is measured with inputs resident in HBM; `e2e` goes through the public multi-rank entry point with
+pinned HOST inputs (H2D inside the timed region) and reads the summary and the draws back to the host.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spatial_gradient posterior-sample x grid-point / s"
+UNIT = "sample*gridpoint/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[4] (the configuration the metric's 2/4/8-GPU figures are quoted on; it fits one GPU)
+    "c5": dict(name="C5: synthetic N=5000 uniform coords, matern2, 100x100 grid", n=5000, cov="matern2", gside=100,
+               phi=(100.0, 200.0), batch=8, g_cpu=16),
+    # BASELINE.json configs[3]
+    "c4": dict(name="C4: synthetic N=2000 uniform coords, gaussian, 60x60 grid", n=2000, cov="gaussian", gside=60,
+               phi=(3000.0, 6000.0), batch=64, g_cpu=32),
+    # BASELINE.json configs[0] (README synthetic)
+    "c1": dict(name="C1: README synthetic N=100, matern2, 19x19 grid", n=100, cov="matern2", gside=19,
+               phi=(10.0, 30.0), batch=1000, g_cpu=361),
+}
+
+
+def ncomp(cov):
+    return 2 if cov == "matern1" else 5
+
+
+def make_inputs(w, S, seed0=0):
+    """Synthetic inputs of SURVEY section 8d (NumPy Philox; shared by the GPU path, the oracle and the CPU baseline)."""
+    P = lambda s: np.random.Generator(np.random.Philox(seed0 + s))   # noqa: E731
+    n, c = w["n"], ncomp(w["cov"])
+    coords = P(1).random((n, 2))
+    gs = np.linspace(0.05, 0.95, w["gside"])
+    grid = np.array([[a, b] for b in gs for a in gs])
+    r3 = P(3)
+    sig2 = r3.uniform(0.5, 2.0, S)
+    phi = r3.uniform(w["phi"][0], w["phi"][1], S)
+    f = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1]))
+    z = (f - f.mean())[None, :] + 0.3 * P(4).standard_normal((S, n))
+    eps = P(5).standard_normal((S, grid.shape[0], c))
+    return coords, grid, phi, sig2, z, eps
+
+
+def flops_per_unit(w):
+    """Algorithmic flops per (sample, grid point) -- SURVEY section 8d: c N^2 (TRMM) + (N^3/3 potrf + N^3/3 trtri
+    + N^2) / G + O(cN)."""
+    n, c, G = w["n"], ncomp(w["cov"]), w["gside"] ** 2
+    return c * n * (n + 1.0) + (c * (c + 1) + 2 * c) * n + (2.0 * n ** 3 / 3.0 + n * n) / G
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- reference arm: the restated reference algorithm on the host cores --------------------------------------
+def run_reference(args, w):
+    from oracle import baseline
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, cores - 1)                       # R/spatial_gradient.R:29-30: detectCores() - 1
+    coords, grid, phi, sig2, z, eps = make_inputs(w, workers)
+    G = grid.shape[0]
+    g_cpu = min(w["g_cpu"], G)
+    vals, walls = [], []
+    for it in range(args.warmup + args.steps):
+        r = baseline.gradient_reference_step(coords, grid, w["cov"], phi, sig2, z, eps, g_cpu, workers)
+        if it >= args.warmup:
+            vals.append(r["units_per_s"])
+            walls.append(r["wall"])
+            last = r
+    value = float(np.median(vals))
+    sample = ("%d forked workers x 1 BLAS thread, 1 sample each, %d of %d grid points; per worker rate = "
+              "G/(t_factor + G*t_grid), t_factor=%.2fs t_grid=%.4fs (mean), summed over workers; restated reference "
+              "algorithm (NumPy+OpenBLAS), not R" % (workers, g_cpu, G, last["t_factor"], last["t_grid"]))
+    hi = baseline.host_info()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "cov_type": w["cov"], "n": w["n"], "grid_points": G},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                             "host": hi},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import spwombling_b200 as spw
+    from spwombling_b200 import device as dev
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    lib = spw.load()
+    lib.spw_set_device(local)
+    n, cov, c = w["n"], w["cov"], ncomp(w["cov"])
+    B = args.batch or w["batch"]
+    npool = 3                                            # distinct sample batches cycled through the steps
+    coords, grid, phi, sig2, z, eps = make_inputs(w, B * npool, seed0=1000 * rank)
+    G = grid.shape[0]
+    coords_d = dev.coords_to_device(coords, device)
+    grid_d = dev.coords_to_device(grid, device)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+    host = [dict(phi=pin(phi[i * B:(i + 1) * B]), sig2=pin(sig2[i * B:(i + 1) * B]), z=pin(z[i * B:(i + 1) * B]),
+                 eps=pin(eps[i * B:(i + 1) * B])) for i in range(npool)]
+    devb = [{k: v.to(device) for k, v in h.items()} for h in host]
+    draws_buf = torch.empty((B, c, G), dtype=torch.float64, device=device)
+    nbatch_sum = 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        d = devb[i % npool]
+        mine = dev.gradient_shard(coords_d, grid_d, cov, d["phi"], d["sig2"], d["z"], d["eps"], out=draws_buf)
+        if world > 1:
+            return dev.gather_shards(mine, B * world)
+        return mine
+
+    def step_e2e(i):
+        h = host[i % npool]
+        d = {k: v.to(device, non_blocking=True) for k, v in h.items()}
+        mine = dev.gradient_shard(coords_d, grid_d, cov, d["phi"], d["sig2"], d["z"], d["eps"], out=draws_buf)
+        full = dev.gather_shards(mine, B * world) if world > 1 else mine
+        if rank == 0:
+            summ = dev.hpd_summary_dev(full, nbatch_sum).cpu()
+            draws_r = dev.draws_to_r_layout(full).cpu()
+            return summ, draws_r
+        return None
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    units_per_step = B * G * world
+    # ---- value: HBM-resident inputs, phase events and clocks sampled during the timed region ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.spw_profile_enable(1)
+    lib.spw_profile_read(None, None, None, 1)
+    spw.launch_count(reset=True)
+    ms_total = timed(step_resident, args.steps, 0)
+    launches = spw.launch_count()
+    ph_ms = (ctypes.c_double * 6)()
+    ph_calls = (ctypes.c_longlong * 6)()
+    main_flops = ctypes.c_double(0.0)
+    lib.spw_profile_read(ctypes.cast(ph_ms, ctypes.c_void_p), ctypes.cast(ph_calls, ctypes.c_void_p),
+                         ctypes.cast(ctypes.byref(main_flops), ctypes.c_void_p), 1)
+    lib.spw_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = units_per_step * args.steps / (ms_total * 1e-3)
+    # ---- e2e: pinned host inputs -> H2D -> shard -> gather -> summary + draws -> D2H ----
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(int(v.numel()) * 8 for v in host[0].values())
+    d2h = (c * 3 * G + B * world * c * G) * 8
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (fused TRMM + Gram + draw) ----
+    peaks = {}
+    for f in ("profiles/FP64_PEAK.json", "MEASURED_PEAKS.json"):
+        p = os.path.join(ROOT, f)
+        if os.path.exists(p):
+            peaks.update(json.load(open(p)))
+    peak_tf = float(peaks.get("fp64_tensor_tflops", 37.0))
+    main_ms, main_calls = ph_ms[5], max(1, ph_calls[5])
+    achieved_tf = main_flops.value / (main_ms * 1e-3) / 1e12 if main_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "main_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    names = ["cov_assemble", "potrf", "trtri", "trmv", "cross_cov", "gradient_main"]
+    phases = {nm: {"ms_per_step": ph_ms[i] / args.steps, "launch_groups": int(ph_calls[i])} for i, nm in enumerate(names)}
+    roofline = {"bound": "tensor", "kernel": "gradient_main_kernel (fused TRMM + Gram + 5x5 chol + draw)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
+                "peak_source": "measured FP64 tensor pipe (DMMA.8x8x4 micro-benchmark, profiles/FP64_PEAK.json; "
+                               "MEASURED_PEAKS.json has no FP64 entry)",
+                "ms_per_launch": main_ms / main_calls, "flops_per_launch": main_flops.value / main_calls,
+                "share_of_step": main_ms / ms_total}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "cov_type": cov, "n": n, "grid_points": G,
+                       "samples_per_rank_per_step": B, "units_per_step": units_per_step,
+                       "flops_per_unit": flops_per_unit(w), "parallelism": "sample-sharded x%d" % world,
+                       "l2": "inputs larger than L2: per step the kernels stream %.1f GB of factors and "
+                             "cross-covariances (L2 is 126 MB); sample batches cycle" %
+                             ((2 * n * n * 8 + c * G * n * 8) * B / 1e9)},
+            "algorithmic_tflops": value * flops_per_unit(w) / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "phases": phases}
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
+    if world == 1 and not args.no_cpu:
+        from oracle import baseline
+        cores = os.cpu_count() or 1
+        workers = max(1, cores - 1)
+        g_cpu = min(w["g_cpu"], G)
+        r = baseline.gradient_reference_step(coords, grid, cov, phi, sig2, z, eps, g_cpu, workers)
+        line["cpu_baseline"] = {"value": r["units_per_s"], "unit": UNIT, "cores": workers, "kind": "port",
+                                "sample": "%d forked workers x 1 BLAS thread (the reference's mclapply shape), 1 sample "
+                                          "each, %d of %d grid points, extrapolated per worker as G/(t_factor + G*t_grid) "
+                                          "with t_factor=%.2fs, t_grid=%.4fs; restated reference algorithm "
+                                          "(NumPy+OpenBLAS), not R" % (workers, g_cpu, G, r["t_factor"], r["t_grid"]),
+                                "host": baseline.host_info()}
+    # ---- secondary metric: hlmBayes_sp MCMC iterations / s at 1 GPU ----
+    if world == 1 and not args.no_hlm:
+        line["hlm"] = bench_hlm(spw, args)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def bench_hlm(spw, args):
+    """hlmBayes_sp iterations/s (BASELINE.json's second metric), N = 5000 matern2 and the README's N = 100."""
+    out = {}
+    for n, niter in ((5000, 6), (100, 600)):
+        rng = np.random.Generator(np.random.Philox(2))
+        coords = rng.random((n, 2))
+        y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
+        r6 = np.random.Generator(np.random.Philox(6))
+        norm, unif = r6.standard_normal(3 * niter), r6.random(3 * niter)
+        kw = dict(y=y, coords=coords, nburn=0, report=max(1, niter // 2), cov_type="matern2", verbose=False)
+        spw.hlmBayes_sp(niter=2, norm=norm, unif=unif, **kw)                     # warm-up (plans, attributes)
+        t0 = time.perf_counter()
+        spw.hlmBayes_sp(niter=niter, norm=norm, unif=unif, **kw)
+        dt = time.perf_counter() - t0
+        its = niter / dt
+        out["n%d" % n] = {"iters_per_s": its, "niter": niter,
+                          "cholesky_tflops": its * 3 * n ** 3 / 3.0 / 1e12,
+                          "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H included); 3 Cholesky "
+                                  "factorisations of order n+1 per iteration"}
+    if not args.no_cpu:
+        from oracle import baseline
+        n = 5000
+        rng = np.random.Generator(np.random.Philox(2))
+        coords = rng.random((n, 2))
+        y = rng.standard_normal(n)
+        dt, _ = baseline.hlm_reference_iteration(coords, y, "matern2")
+        out["n5000"]["cpu_baseline_iters_per_s"] = 1.0 / dt
+        out["n5000"]["cpu_baseline_note"] = ("restated reference iteration (3 x dpotrf + dpotri + quadratic form, "
+                                             "NumPy+OpenBLAS all threads), not R")
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="posterior samples per rank per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-hlm", action="store_true", help="skip the hlmBayes_sp secondary metric")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,13 @@ int spw_set_workspace_limit(long long bytes);
 /* number of CUDA kernel launches issued by this library since the last call with reset != 0 */
 long long spw_launch_count(int reset);
 
+/* Phase timing of the spatial_gradient pipeline with CUDA events on the launching stream (off by default).
+ * ms / calls have 6 entries: 0 covariance assembly, 1 Cholesky, 2 triangular inverse, 3 Linv z,
+ * 4 cross-covariance assembly, 5 fused TRMM + Gram + draw kernel; main_flops = algorithmic flops of phase 5
+ * (per launch: samples x grid points x (c n (n+1) + (c (c+1) + 2 c) n)). */
+int spw_profile_enable(int on);
+int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset);
+
 /* covariance kernels ----------------------------------------------------------------------------
  * spw_cov: as.matrix(dist(coords)) fused with cov_gaussian / cov_matern1 / cov_matern2
  *   replaces R/hlmBayes_sp.R:38 + R/cov_gaussian.R:14, R/cov_matern1.R:14, R/cov_matern2.R:14.

@@ -27,6 +27,8 @@ SIGNATURES = {
     "spw_shutdown": (c_int, []),
     "spw_set_workspace_limit": (c_int, [c_ll]),
     "spw_launch_count": (c_ll, [c_int]),
+    "spw_profile_enable": (c_int, [c_int]),
+    "spw_profile_read": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "spw_cov": (c_int, [c_int, c_int, c_vp, c_dbl, c_dbl, c_vp]),
     "spw_cov_delta": (c_int, [c_int, c_ll, c_vp, c_dbl, c_dbl, c_vp]),
     "spw_cross_cov": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_dbl, c_vp]),

@@ -11,6 +11,9 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libspwombling.so")
 SOURCES = ["api.cu", "cov.cu", "linalg.cu", "gradient.cu", "summary.cu", "hlm.cu"]
+# cov.cu is compiled without FMA contraction: its elementwise formulas then round exactly like the reference's
+# R arithmetic (and K[i][j] == K[j][i] bit for bit, whichever thread computes it)
+EXTRA_FLAGS = {"cov.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 
@@ -31,7 +34,7 @@ def build(force=False, verbose=False):
         o = s[:-3] + ".o"
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_time):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + EXTRA_FLAGS.get(src, []) + ["-c", s, "-o", o]
             procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
             rebuilt = True
     for src, cmd, p in procs:

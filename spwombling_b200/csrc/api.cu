@@ -34,6 +34,48 @@ void set_error(const char* fmt, ...) {
   memcpy(g_error, tl_error, sizeof(g_error));
 }
 
+// ---- optional phase timing (CUDA events on the launching stream) ----------------------------------------
+enum Phase { PH_COV = 0, PH_POTRF, PH_TRTRI, PH_TRMV, PH_CROSS, PH_MAIN, PH_COUNT };
+static int g_profile = 0;
+static double g_phase_ms[PH_COUNT] = {0};
+static long long g_phase_calls[PH_COUNT] = {0};
+static double g_main_flops = 0.0;          // algorithmic flops of the timed gradient_main launches
+static std::mutex g_prof_mu;
+
+struct PhaseTimer {
+  struct Rec { int phase; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  cudaStream_t st;
+  explicit PhaseTimer(cudaStream_t s) : st(s) {}
+  void begin(int phase) {
+    if (!g_profile) return;
+    Rec r;
+    r.phase = phase;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void end() {
+    if (!g_profile || recs.empty()) return;
+    cudaEventRecord(recs.back().e1, st);
+  }
+  void collect() {   // call after the stream has been synchronised
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        g_phase_ms[r.phase] += ms;
+        g_phase_calls[r.phase] += 1;
+      }
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    recs.clear();
+  }
+  ~PhaseTimer() { collect(); }
+};
+
 // ---- per-device context -----------------------------------------------------------------------------
 struct DeviceCtx {
   cudaStream_t stream = nullptr;
@@ -154,18 +196,29 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   std::vector<int> h_status(2 * (size_t)B);
   MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld}, AT{At, ld, (long long)gc * c * ld};
 
+  PhaseTimer pt(st);
   for (int s0 = 0; s0 < S; s0 += B) {
     const int nb = std::min(B, S - s0);
     SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 2 * B, st));
     // K = cov(phi_s, sig2 = 1), no nugget            R/spatial_gradient.R:215,264,303
+    pt.begin(PH_COV);
     SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, nullptr, 1, L, nb, 1, st));
+    pt.end();
     // chol(K) and its triangular inverse            R/spatial_gradient.R:216,265,304
+    pt.begin(PH_POTRF);
     SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status, st));
+    pt.end();
+    pt.begin(PH_TRTRI);
     SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    pt.end();
+    pt.begin(PH_TRMV);
     SPW_TRY(trmv_lower_batched(n, Linv, z + (long long)s0 * ldz, ldz, vb, ld, nb, st));
+    pt.end();
     for (int g0 = 0; g0 < G; g0 += gc) {
       const int ng = std::min(gc, G - g0);
+      pt.begin(PH_CROSS);
       SPW_TRY(cross_cov_batched(type, n, cx, cy, g0, ng, gx, gy, phi + s0, AT, nb, st));
+      pt.end();
       GradParams P;
       P.linv = Linv;
       P.at = AT;
@@ -183,10 +236,17 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
       P.g_count = ng;
       P.g_total = G;
       P.s_begin = s0;
+      pt.begin(PH_MAIN);
       SPW_TRY(gradient_main_launch(type, P, nb, st));
+      pt.end();
+      if (g_profile) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_main_flops += (double)nb * ng * ((double)c * n * ((double)n + 1.0) + (double)(c * (c + 1) + 2 * c) * n);
+      }
     }
     SPW_CUDA(cudaMemcpyAsync(h_status.data(), status, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost, st));
     SPW_CUDA(cudaStreamSynchronize(st));
+    pt.collect();
     for (int b = 0; b < nb; ++b) {
       if (h_status[b]) {
         if (info) { info[0] = s0 + b + 1; info[1] = h_status[b]; info[2] = 1; }
@@ -250,6 +310,26 @@ long long spw_launch_count(int reset) {
   long long v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+int spw_profile_enable(int on) {
+  g_profile = on;
+  return SPW_OK;
+}
+
+int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < PH_COUNT; ++i) {
+    if (ms) ms[i] = g_phase_ms[i];
+    if (calls) calls[i] = g_phase_calls[i];
+    if (reset) {
+      g_phase_ms[i] = 0.0;
+      g_phase_calls[i] = 0;
+    }
+  }
+  if (main_flops) *main_flops = g_main_flops;
+  if (reset) g_main_flops = 0.0;
+  return SPW_OK;
 }
 
 int spw_shutdown(void) {

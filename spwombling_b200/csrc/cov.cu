@@ -44,7 +44,8 @@ cov_assemble_kernel(int n, const double* __restrict__ cx, const double* __restri
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const double dx = sx_r[lr] - sx_c[lc + e], dy = sy_r[lr] - sy_c[lc + e];
-      const double d = sqrt(dx * dx + dy * dy);
+      // (dx*dx) + (dy*dy), each product rounded: bit-identical to R's dist() and symmetric in (r, c)
+      const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
       double val = s2 * cov_rho<TYPE>(ph, d);
       if (r == c + e) val = s2 + ng;   // exact zero distance on the diagonal
       v[e] = val;
@@ -117,7 +118,7 @@ cross_cov_kernel(int n, const double* __restrict__ cx, const double* __restrict_
   for (int e = 0; e < 2; ++e) {
     const int kk = (k + e < n) ? k + e : k;
     const double d1 = cx[kk] - g1, d2 = cy[kk] - g2;          // delta.s0 = coords - grid (R/spatial_gradient.R:46)
-    const double d = sqrt(d1 * d1 + d2 * d2);                 // dist.s0 (R/spatial_gradient.R:45)
+    const double d = sqrt(__dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2)));   // dist.s0 (R/spatial_gradient.R:45)
     if constexpr (TYPE == 0) {
       const double e0 = exp(-ph * (d * d));
       const double t = 2.0 * ph * e0;
