@@ -82,6 +82,8 @@ struct DeviceCtx {
   std::map<std::pair<int, int>, LinalgPlan*> plans;
   void* ws = nullptr;          // grow-only workspace
   size_t ws_bytes = 0;
+  void* ws2 = nullptr;         // grow-only scratch of the summary kernels
+  size_t ws2_bytes = 0;
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_ctx_mu;
@@ -122,6 +124,18 @@ static int get_workspace(DeviceCtx& c, size_t bytes, void** out) {
     c.ws_bytes = bytes;
   }
   *out = c.ws;
+  return SPW_OK;
+}
+
+static int get_scratch(DeviceCtx& c, size_t bytes, void** out) {
+  if (bytes > c.ws2_bytes) {
+    if (c.ws2) SPW_CUDA(cudaFree(c.ws2));
+    c.ws2 = nullptr;
+    c.ws2_bytes = 0;
+    SPW_CUDA(cudaMalloc(&c.ws2, bytes));
+    c.ws2_bytes = bytes;
+  }
+  *out = c.ws2;
   return SPW_OK;
 }
 
@@ -197,6 +211,8 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld}, AT{At, ld, (long long)gc * c * ld};
 
   PhaseTimer pt(st);
+  const char* env_main = getenv("SPW_MAIN");
+  const bool use_tma = !(env_main && env_main[0] == '0');
   for (int s0 = 0; s0 < S; s0 += B) {
     const int nb = std::min(B, S - s0);
     SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 2 * B, st));
@@ -237,7 +253,8 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
       P.g_total = G;
       P.s_begin = s0;
       pt.begin(PH_MAIN);
-      SPW_TRY(gradient_main_launch(type, P, nb, st));
+      if (use_tma) SPW_TRY(gradient_tma_launch(type, P, nb, st));
+      else SPW_TRY(gradient_main_launch(type, P, nb, st));
       pt.end();
       if (g_profile) {
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -348,6 +365,9 @@ int spw_shutdown(void) {
     if (c.ws) cudaFree(c.ws);
     c.ws = nullptr;
     c.ws_bytes = 0;
+    if (c.ws2) cudaFree(c.ws2);
+    c.ws2 = nullptr;
+    c.ws2_bytes = 0;
     if (c.stream) cudaStreamDestroy(c.stream);
     c.stream = nullptr;
   }
@@ -675,7 +695,9 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
   }
   if (out_summary) {
     SPW_TRY(dsum.alloc(sizeof(double) * 3 * (size_t)g * c));
-    SPW_TRY(hpd_summary_dev(S, g, c, nbatch, prob, dall.as<double>(), dsum.as<double>(), rst));
+    void* scratch;
+    SPW_TRY(get_scratch(*rctx, hpd_scratch_bytes(S, g, c, nbatch), &scratch));
+    SPW_TRY(hpd_summary_dev(S, g, c, nbatch, prob, dall.as<double>(), dsum.as<double>(), scratch, rst));
     SPW_CUDA(cudaMemcpyAsync(out_summary, dsum.p, sizeof(double) * 3 * (size_t)g * c, cudaMemcpyDeviceToHost, rst));
   }
   if (out_draws) {
@@ -694,7 +716,9 @@ int spw_hpd_summary_dev(int S, int g, int ncomp, int nbatch, double prob, const 
   DeviceCtx* ctx;
   SPW_TRY(get_ctx(&ctx));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return hpd_summary_dev(S, g, ncomp, nbatch, prob, draws_dev, out_dev, st);
+  void* scratch;
+  SPW_TRY(get_scratch(*ctx, hpd_scratch_bytes(S, g, ncomp, nbatch), &scratch));
+  return hpd_summary_dev(S, g, ncomp, nbatch, prob, draws_dev, out_dev, scratch, st);
 }
 
 int spw_draws_to_r_layout_dev(int S, int g, int ncomp, const double* draws_dev, double* out_dev, void* stream) {
@@ -716,7 +740,9 @@ int spw_hpd_summary(int S, int g, int nbatch, double prob, const double* draws, 
   SPW_CUDA(cudaMemcpyAsync(din.p, draws, sizeof(double) * (size_t)S * g, cudaMemcpyHostToDevice, st));
   // R layout [g][S] (S contiguous) -> [S][1][g]
   SPW_TRY(transpose_batched(g, S, din.as<double>(), S, 0, dt.as<double>(), g, 0, 1, st));
-  SPW_TRY(hpd_summary_dev(S, g, 1, nbatch, prob, dt.as<double>(), dout.as<double>(), st));
+  void* scratch;
+  SPW_TRY(get_scratch(*ctx, hpd_scratch_bytes(S, g, 1, nbatch), &scratch));
+  SPW_TRY(hpd_summary_dev(S, g, 1, nbatch, prob, dt.as<double>(), dout.as<double>(), scratch, st));
   SPW_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * 3 * (size_t)g, cudaMemcpyDeviceToHost, st));
   SPW_CUDA(cudaStreamSynchronize(st));
   return SPW_OK;

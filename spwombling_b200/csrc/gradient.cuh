@@ -22,6 +22,9 @@ struct GradParams {
   int s_begin;
 };
 
+// cp.async / __syncthreads version (gradient.cu; kept as a cross-check, SPW_MAIN=0)
 int gradient_main_launch(int type, const GradParams& P, int batch, cudaStream_t st);
+// TMA + mbarrier + warp-specialised version (gradient_tma.cu; default)
+int gradient_tma_launch(int type, const GradParams& P, int batch, cudaStream_t st);
 
 }  // namespace spw

@@ -124,27 +124,29 @@ int hpd_gap(int nb, double prob) {
   return std::max(1, std::min(nb - 1, r));
 }
 
+size_t hpd_scratch_bytes(int S, int G, int ncomp, int nbatch) {
+  const size_t nb = (size_t)std::min(std::max(nbatch, 1), std::max(S, 1)) + 2;
+  return sizeof(int) * (nb + 2) + 256 + 2 * sizeof(double) * (size_t)ncomp * nb * G + 512;
+}
+
 int hpd_summary_dev(int S, int G, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
-                    cudaStream_t st) {
+                    void* scratch, cudaStream_t st) {
   if (S < 1 || G < 1 || nbatch < 1) { set_error("hpd_summary: bad sizes"); return SPW_ERR_ARG; }
   std::vector<int> starts = batch_starts(S, nbatch);
   const int nb = (int)starts.size() - 1;
   if (nb < 2) { set_error("hpd_summary: obj must have nsamp > 1 (need at least two batches)"); return SPW_ERR_ARG; }
   if (nb > 65535) { set_error("hpd_summary: too many batches"); return SPW_ERR_ARG; }
-  int* d_starts = nullptr;
-  double *d_med = nullptr, *d_sorted = nullptr;
-  SPW_CUDA(cudaMallocAsync(&d_starts, sizeof(int) * starts.size(), st));
-  SPW_CUDA(cudaMallocAsync(&d_med, sizeof(double) * (size_t)ncomp * nb * G, st));
-  SPW_CUDA(cudaMallocAsync(&d_sorted, sizeof(double) * (size_t)ncomp * nb * G, st));
+  char* base = (char*)scratch;
+  int* d_starts = (int*)base;
+  size_t off = (sizeof(int) * starts.size() + 255) / 256 * 256;
+  double* d_med = (double*)(base + off);
+  double* d_sorted = d_med + (size_t)ncomp * nb * G;
   SPW_CUDA(cudaMemcpyAsync(d_starts, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaStreamSynchronize(st));   // the host vector must outlive the copy (pageable source)
   batch_median_kernel<<<dim3(ceil_div(G, 128), nb, ncomp), 128, 0, st>>>(G, ncomp, nb, d_starts, draws_dev, d_med);
   SPW_LAUNCHED();
   hpd_kernel<<<dim3(ceil_div(G, 128), ncomp), 128, 0, st>>>(G, nb, hpd_gap(nb, prob), d_med, d_sorted, out_dev);
   SPW_LAUNCHED();
-  SPW_CUDA(cudaStreamSynchronize(st));   // starts vector must outlive the async copy
-  SPW_CUDA(cudaFreeAsync(d_starts, st));
-  SPW_CUDA(cudaFreeAsync(d_med, st));
-  SPW_CUDA(cudaFreeAsync(d_sorted, st));
   return SPW_OK;
 }
 

@@ -11,8 +11,10 @@ std::vector<int> batch_starts(int S, int nbatch);
 int hpd_gap(int nb, double prob);
 
 // draws_dev [S][ncomp][G] -> out_dev [ncomp][3][G] (estimate, lower, upper)
+// scratch: device buffer of at least hpd_scratch_bytes(...) bytes
+size_t hpd_scratch_bytes(int S, int G, int ncomp, int nbatch);
 int hpd_summary_dev(int S, int G, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
-                    cudaStream_t st);
+                    void* scratch, cudaStream_t st);
 
 // batch of row-major [rows][cols] -> [cols][rows]
 int transpose_batched(int rows, int cols, const double* in, long long in_ld, long long in_bstride, double* out,
