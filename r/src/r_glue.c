@@ -1,0 +1,73 @@
+/*
+ * r_glue.c -- .Call shim between the unchanged R functions of spWombling and libspwombling (include/spwombling.h).
+ * Marshalling only: every wrapper checks types, allocates the R result vectors, calls one C-ABI entry point with
+ * plain pointers, and turns a non-zero status into an R error (the reference stops in chol() there).
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no R headers (Rinternals.h).  Build inside the
+ * package with  PKG_LIBS = -L$(SPW_LIB_DIR) -lspwombling -lcudart  and  useDynLib(spWombling, .registration = TRUE).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include "spwombling.h"
+
+static void spw_stop(int rc) {
+  if (rc != SPW_OK) Rf_error("spWombling (GPU): %s", spw_last_error());
+}
+
+/* cov_*(Delta, phi, sig2)  --  R/cov_gaussian.R:10, R/cov_matern1.R:10, R/cov_matern2.R:10 */
+SEXP spw_r_cov_delta(SEXP type, SEXP delta, SEXP phi, SEXP sig2) {
+  SEXP out = PROTECT(Rf_duplicate(delta));
+  spw_stop(spw_cov_delta(Rf_asInteger(type), (long long)XLENGTH(delta), REAL(delta), Rf_asReal(phi),
+                         Rf_asReal(sig2), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+/* hlmBayes_sp hot loop  --  R/hlmBayes_sp.R:99-302.  norm/unif are drawn by the R host in the reference's order. */
+SEXP spw_r_hlm_run(SEXP coords, SEXP y, SEXP type, SEXP niter, SEXP nburn, SEXP report, SEXP hyper /* a.s,b.s,a.t,b.t,lo,hi */,
+                   SEXP norm, SEXP unif, SEXP want_trgt) {
+  const int n = Rf_length(y), it = Rf_asInteger(niter), rep = Rf_asInteger(report), nrep = it / rep;
+  const double* h = REAL(hyper);
+  SEXP ans = PROTECT(Rf_allocVector(VECSXP, 6));
+  SEXP sig2 = PROTECT(Rf_allocVector(REALSXP, it)), tau2 = PROTECT(Rf_allocVector(REALSXP, it));
+  SEXP phi = PROTECT(Rf_allocVector(REALSXP, it)), trgt = PROTECT(Rf_allocVector(REALSXP, it + 1));
+  SEXP acc = PROTECT(Rf_allocMatrix(REALSXP, nrep > 0 ? nrep : 1, 3)), tun = PROTECT(Rf_allocMatrix(REALSXP, nrep > 0 ? nrep : 1, 3));
+  int info[4];
+  spw_stop(spw_hlm_run(n, REAL(coords), REAL(y), Rf_asInteger(type), it, Rf_asInteger(nburn), rep, h[0], h[1], h[2], h[3],
+                       h[4], h[5], REAL(norm), REAL(unif), Rf_asLogical(want_trgt), REAL(sig2), REAL(tau2), REAL(phi),
+                       REAL(trgt), REAL(acc), REAL(tun), info));
+  SET_VECTOR_ELT(ans, 0, sig2); SET_VECTOR_ELT(ans, 1, tau2); SET_VECTOR_ELT(ans, 2, phi);
+  SET_VECTOR_ELT(ans, 3, trgt); SET_VECTOR_ELT(ans, 4, acc);  SET_VECTOR_ELT(ans, 5, tun);
+  UNPROTECT(7);
+  return ans;
+}
+
+/* spatial_gradient hot loop + summary  --  R/spatial_gradient.R:199-419 */
+SEXP spw_r_gradient_run(SEXP type, SEXP coords, SEXP grid, SEXP phi, SEXP sig2, SEXP z, SEXP eps, SEXP ngpu, SEXP nbatch,
+                        SEXP want_mcmc) {
+  const int ty = Rf_asInteger(type), n = Rf_nrows(coords), g = Rf_nrows(grid), S = Rf_length(phi);
+  const int c = (ty == SPW_COV_MATERN1) ? 2 : 5, mc = Rf_asLogical(want_mcmc);
+  SEXP ans = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP summ = PROTECT(Rf_alloc3DArray(REALSXP, g, 3, c));
+  SEXP draws = PROTECT(mc ? Rf_alloc3DArray(REALSXP, S, g, c) : Rf_allocVector(REALSXP, 0));
+  int info[4];
+  spw_stop(spw_gradient_run(ty, n, REAL(coords), g, REAL(grid), S, REAL(phi), REAL(sig2), REAL(z), REAL(eps),
+                            Rf_asInteger(ngpu), Rf_asInteger(nbatch), 0.95, mc ? REAL(draws) : NULL, REAL(summ), NULL, NULL,
+                            info));
+  SET_VECTOR_ELT(ans, 0, summ); SET_VECTOR_ELT(ans, 1, draws);
+  UNPROTECT(3);
+  return ans;
+}
+
+static const R_CallMethodDef call_methods[] = {
+  {"spw_r_cov_delta", (DL_FUNC)&spw_r_cov_delta, 4},
+  {"spw_r_hlm_run", (DL_FUNC)&spw_r_hlm_run, 10},
+  {"spw_r_gradient_run", (DL_FUNC)&spw_r_gradient_run, 10},
+  {NULL, NULL, 0}
+};
+
+void R_init_spWombling(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
