@@ -1,12 +1,14 @@
 // C ABI of libspwombling: argument checking, device workspaces, host<->device marshalling of R-layout
 // arrays, and the per-shard driver of the spatial_gradient pipeline.  See include/spwombling.h.
 #include <cstdarg>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "../../include/spwombling.h"
@@ -39,11 +41,17 @@ enum Phase { PH_COV = 0, PH_POTRF, PH_TRTRI, PH_TRMV, PH_CROSS, PH_MAIN, PH_COUN
 static int g_profile = 0;
 static double g_phase_ms[PH_COUNT] = {0};
 static long long g_phase_calls[PH_COUNT] = {0};
+static double g_phase_host_ms[PH_COUNT] = {0};   // host wall time spent issuing each phase
 static double g_main_flops = 0.0;          // algorithmic flops of the timed gradient_main launches
 static std::mutex g_prof_mu;
 
 struct PhaseTimer {
-  struct Rec { int phase; cudaEvent_t e0, e1; };
+  struct Rec { int phase; cudaEvent_t e0, e1; double h0, h1; };
+  static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
   std::vector<Rec> recs;
   cudaStream_t st;
   explicit PhaseTimer(cudaStream_t s) : st(s) {}
@@ -54,11 +62,13 @@ struct PhaseTimer {
     cudaEventCreate(&r.e0);
     cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
+    r.h0 = r.h1 = now_ms();
     recs.push_back(r);
   }
   void end() {
     if (!g_profile || recs.empty()) return;
     cudaEventRecord(recs.back().e1, st);
+    recs.back().h1 = now_ms();
   }
   void collect() {   // call after the stream has been synchronised
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -67,6 +77,7 @@ struct PhaseTimer {
       if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
         g_phase_ms[r.phase] += ms;
         g_phase_calls[r.phase] += 1;
+        g_phase_host_ms[r.phase] += r.h1 - r.h0;
       }
       cudaEventDestroy(r.e0);
       cudaEventDestroy(r.e1);
@@ -79,7 +90,7 @@ struct PhaseTimer {
 // ---- per-device context -----------------------------------------------------------------------------
 struct DeviceCtx {
   cudaStream_t stream = nullptr;
-  std::map<std::pair<int, int>, LinalgPlan*> plans;
+  std::map<std::tuple<int, int, int>, LinalgPlan*> plans;
   void* ws = nullptr;          // grow-only workspace
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
@@ -98,13 +109,13 @@ static int get_ctx(DeviceCtx** out) {
   return SPW_OK;
 }
 
-static int get_plan(DeviceCtx& c, int n, int extra, const LinalgPlan** out) {
+static int get_plan(DeviceCtx& c, int n, int extra, int single, const LinalgPlan** out) {
   std::lock_guard<std::mutex> lk(g_ctx_mu);
-  auto key = std::make_pair(n, extra);
+  auto key = std::make_tuple(n, extra, single);
   auto it = c.plans.find(key);
   if (it == c.plans.end()) {
     LinalgPlan* p = new LinalgPlan();
-    int rc = plan_build(*p, n, extra);
+    int rc = plan_build(*p, n, extra, single);
     if (rc != SPW_OK) {
       delete p;
       return rc;
@@ -177,19 +188,25 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   if (S == 0) return SPW_OK;
   DeviceCtx* ctx;
   SPW_TRY(get_ctx(&ctx));
-  const LinalgPlan* plan;
-  SPW_TRY(get_plan(*ctx, n, 0, &plan));
   const int c = ncomp_of(type);
   const long long ld = pad_ld(n);
-  const int nblk = plan->nblk;
+  const int nblk = ceil_div(n, NB);
   // workspace sizing: batch B samples, grid chunk gc
   const size_t mat = (size_t)n * ld * sizeof(double);
   const size_t per_sample_fixed = 2 * mat + (size_t)ld * sizeof(double) + (size_t)nblk * NB * NB * sizeof(double) + 64;
   const size_t at_per_g = (size_t)c * ld * sizeof(double);
-  const size_t budget = workspace_budget();
+  // the (B, gc) decision is cached per problem shape so that repeated calls skip cudaMemGetInfo
+  struct ShapeKey { int type, n, G, S; size_t limit; int B, gc; };
+  static thread_local ShapeKey last = {-1, 0, 0, 0, 0, 0, 0};
+  const bool reuse = (last.type == type && last.n == n && last.G == G && last.S == S && last.limit == (size_t)g_ws_limit &&
+                      ctx->ws_bytes > 0);
+  const size_t budget = reuse ? 0 : workspace_budget();
   int gc = std::min(G, 65535);
   int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / (per_sample_fixed + at_per_g * gc));
-  if (B < std::min(S, 16)) {   // not enough room for the whole grid at a useful batch size: chunk the grid
+  if (reuse) {
+    B = last.B;
+    gc = last.gc;
+  } else if (B < std::min(S, 16)) {   // not enough room for the whole grid at a useful batch size: chunk the grid
     B = std::min(S, 16);
     while (B > 1 && per_sample_fixed * B > budget / 2) B /= 2;
     const size_t left = budget > per_sample_fixed * B ? budget - per_sample_fixed * B : 0;
@@ -197,6 +214,9 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
     gc = gc / 16 * 16;
     if (gc < 16) { set_error("spw_gradient: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
   }
+  last = ShapeKey{type, n, G, S, (size_t)g_ws_limit, B, gc};
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 0, B < 4 ? 1 : 0, &plan));
   const size_t total = (per_sample_fixed + at_per_g * gc) * B + 4096;
   void* wsp;
   SPW_TRY(get_workspace(*ctx, total, &wsp));
@@ -339,9 +359,13 @@ int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset
   for (int i = 0; i < PH_COUNT; ++i) {
     if (ms) ms[i] = g_phase_ms[i];
     if (calls) calls[i] = g_phase_calls[i];
+    if (getenv("SPW_PROFILE_VERBOSE") && g_phase_calls[i])
+      fprintf(stderr, "[spw] phase %d: gpu %.3f ms, host issue %.3f ms, %lld groups\n", i, g_phase_ms[i],
+              g_phase_host_ms[i], g_phase_calls[i]);
     if (reset) {
       g_phase_ms[i] = 0.0;
       g_phase_calls[i] = 0;
+      g_phase_host_ms[i] = 0.0;
     }
   }
   if (main_flops) *main_flops = g_main_flops;
@@ -447,7 +471,7 @@ int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) 
   SPW_TRY(get_ctx(&ctx));
   cudaStream_t st = ctx->stream;
   const LinalgPlan* plan;
-  SPW_TRY(get_plan(*ctx, n, 0, &plan));
+  SPW_TRY(get_plan(*ctx, n, 0, 1, &plan));
   const long long ld = pad_ld(n);
   DevBuf dm, dd, ds, dl;
   SPW_TRY(dm.alloc(sizeof(double) * n * ld));
@@ -494,7 +518,7 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   SPW_TRY(get_ctx(&ctx));
   cudaStream_t st = ctx->stream;
   const LinalgPlan* plan;
-  SPW_TRY(get_plan(*ctx, n, 1, &plan));
+  SPW_TRY(get_plan(*ctx, n, 1, 1, &plan));
   const long long ld = pad_ld(n);
   const int nrep = niter / report;
   DevBuf dc, dy, dnorm, dunif, dL, dd, ds, dstate, dout;

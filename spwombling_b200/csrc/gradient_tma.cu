@@ -13,9 +13,8 @@
 //   * 8 consumer warps (2 per SM sub-partition) own 32 x (BN/2) accumulator tiles; each warp folds its finished
 //     row block into its own Gram / mean accumulators through a private staging buffer (warp-local, no CTA sync);
 //     the four row-groups are summed in a fixed order at the very end (deterministic).
-#include <cuda.h>
 #include "gradient.cuh"
-#include "gemm_nt.cuh"
+#include "tma.cuh"
 
 namespace spw {
 
@@ -45,40 +44,6 @@ struct TCfg {
   static constexpr size_t TOTAL = PIPE_BYTES + STG_BYTES + BAR_BYTES + 128;
   static_assert(size_t(T_CONSUMER_WARPS) * NIT_W * sizeof(double) <= PIPE_BYTES, "final reduction aliases the ring");
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
-                                            unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 struct TmaParams {
   const double* v;         // [batch][ldv]
@@ -115,7 +80,7 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], T_CONSUMER_WARPS);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
 
@@ -341,44 +306,6 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode_fn(EncodeTiledFn* out) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    SPW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || !p) {
-      set_error("cuTensorMapEncodeTiled is not available in this driver");
-      return SPW_ERR_CUDA;
-    }
-    fn = (EncodeTiledFn)p;
-  }
-  *out = fn;
-  return SPW_OK;
-}
-
-// rank-3 map over a batch of row-major matrices: dims (cols, rows, batch), box (BK + 4, box_rows, 1)
-int make_map(CUtensorMap* tm, const MatView& M, int cols, int rows, int batch, int box_rows) {
-  EncodeTiledFn enc;
-  SPW_TRY(get_encode_fn(&enc));
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)M.ld * sizeof(double), (cuuint64_t)M.stride * sizeof(double)};
-  cuuint32_t box[3] = {(cuuint32_t)T_LDS, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)M.p, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): cols=%d rows=%d batch=%d ld=%lld", (int)r, cols, rows, batch, M.ld);
-    return SPW_ERR_CUDA;
-  }
-  return SPW_OK;
-}
-
 }  // namespace
 
 int gradient_tma_launch(int type, const GradParams& G, int batch, cudaStream_t st) {
@@ -400,8 +327,8 @@ int gradient_tma_launch(int type, const GradParams& G, int batch, cudaStream_t s
     attr_set[dev & 63][type] = true;
   }
   CUtensorMap tmA, tmB;
-  SPW_TRY(make_map(&tmA, G.linv, G.n, G.n, batch, T_BM));
-  SPW_TRY(make_map(&tmB, G.at, G.n, G.g_count * ncomp, batch, bn));
+  SPW_TRY(make_tensor_map(&tmA, G.linv, G.n, G.n, batch, T_LDS, T_BM));
+  SPW_TRY(make_tensor_map(&tmB, G.at, G.n, G.g_count * ncomp, batch, T_LDS, bn));
   TmaParams P;
   P.v = G.v; P.ldv = G.ldv; P.phi = G.phi; P.sig2 = G.sig2; P.eps = G.eps;
   P.out_draws = G.out_draws; P.out_mean = G.out_mean; P.out_var = G.out_var; P.status = G.status;

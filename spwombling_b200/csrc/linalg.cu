@@ -1,4 +1,4 @@
-// Batched blocked Cholesky (right-looking, NB = 64 diagonal blocks, 128x128 DMMA trailing tiles) and
+// Batched blocked Cholesky (right-looking, NB = 64 diagonal blocks inside 256-wide outer blocks, 128x128 DMMA tiles) and
 // level-synchronous divide-and-conquer triangular inverse, both driven by precomputed tile task lists.
 // Replaces the LAPACK calls the reference reaches through base R:
 //   chol()      R/hlmBayes_sp.R:99,114,140,181; R/spatial_gradient.R:216,265,304   (dpotrf)
@@ -6,58 +6,150 @@
 #include <algorithm>
 #include <cstring>
 #include "linalg.cuh"
-#include "gemm_nt.cuh"
+#include "tma.cuh"
 
 namespace spw {
 
-using GemmCfg = NtCfg<128, 128, 16, 4, 4, 2>;   // 8 warps, warp tile 32 x 64
+// ---------------------------------------------------------------------------------------------------
+// Task-driven NT GEMM on the FP64 tensor pipe: one CTA per (task, batch entry), BM x BN output tile, 8 warps (4 x 2).
+// The A and B k-tiles arrive by TMA (boxes of 36 x BM and 36 x BN doubles: 32 columns used + the 4-double pad that
+// keeps the DMMA fragment loads conflict-free) into a ring guarded by mbarriers; the load of tile kt+STAGES-1 is
+// issued by one lane of warp (kt mod 8) once tile kt has landed, so no warp is dedicated to loading (a 9th warp
+// would be allocated as 12 and cap the registers at 168) and there is no CTA barrier in the loop.  Rows / columns of
+// a box outside the task are either other matrix data (their accumulators are not stored) or outside the tensor
+// (zero-filled by TMA), so the only masking left is the triangular one.
+//   L: 128 x 128, 3 stages, 1 CTA/SM   (long-k products of the triangular inverse)
+//   M: 128 x  64, 2 stages, 2 CTA/SM   (Cholesky panel / trailing updates: the second CTA hides the C read-modify-write)
+//   S:  64 x  64, 3 stages, 2 CTA/SM   (latency-critical panel steps of a single matrix)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+constexpr int G_BK = 32, G_LDS = G_BK + 4, G_CW = 8, G_THREADS = 32 * G_CW;
 
-// ---------------------------------------------------------------------------------------------------
-// Task-driven NT GEMM: one CTA per (task, batch entry).
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GemmCfg::NTHREADS, 1)
-gemm_tasks_kernel(const GemmTask* __restrict__ tasks, MatView A, MatView B, MatView C, MatView CT, double alpha) {
-  extern __shared__ __align__(16) double smem[];
+template <int BM_, int BN_, int STAGES_, int MINB_>
+struct GCfg {
+  static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int WM = BM / 4, WN = BN / 2, MF = WM / 8, NF = WN / 8;
+  static constexpr int A_STAGE = BM * G_LDS, B_STAGE = BN * G_LDS, STAGE = A_STAGE + B_STAGE;
+  static constexpr uint32_t STAGE_BYTES = STAGE * sizeof(double);
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * STAGES * sizeof(unsigned long long) + 64;
+};
+using GCfgL = GCfg<128, 128, 3, 1>;
+using GCfgM = GCfg<128, 64, 2, 2>;
+using GCfgS = GCfg<64, 64, 3, 2>;
+}  // namespace
+
+template <class Cfg>
+__global__ void __launch_bounds__(G_THREADS, Cfg::MINB)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmTask* __restrict__ tasks, MatView C, MatView CT, double alpha) {
+  extern __shared__ __align__(128) unsigned char gsm[];
+  double* pipe = reinterpret_cast<double*>(gsm);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(gsm + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
+  unsigned long long* empty = full + Cfg::STAGES;
   const GemmTask t = tasks[blockIdx.x];
-  const long long b = blockIdx.y;
-  const double* Ap = A.p + b * A.stride + (long long)t.a_row * A.ld + t.a_col;
-  const double* Bp = B.p + b * B.stride + (long long)t.b_row * B.ld + t.b_col;
-  double acc[GemmCfg::MF][GemmCfg::NF][2];
-#pragma unroll
-  for (int i = 0; i < GemmCfg::MF; ++i)
-#pragma unroll
-    for (int j = 0; j < GemmCfg::NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  TriMask tm{t.a_tri, t.a_lim0, t.b_tri, t.b_lim0};
-  nt_mainloop<GemmCfg>(Ap, A.ld, t.m, Bp, B.ld, t.n, t.k, tm, smem, acc);
-
+  const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int warp_m = warp % GemmCfg::WARPS_M, warp_n = warp / GemmCfg::WARPS_M;
+  const int nkt = (t.k + G_BK - 1) / G_BK;
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], G_CW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int kt) {   // one thread: wait for the slot, arm the barrier, launch the two tile loads
+    const int s = kt % Cfg::STAGES;
+    mbar_wait(&empty[s], ((kt / Cfg::STAGES) & 1) ^ 1);
+    double* st = pipe + (size_t)s * Cfg::STAGE;
+    mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+    tma_load_3d(st, &tmA, t.a_col + kt * G_BK, t.a_row, b, &full[s]);
+    tma_load_3d(st + Cfg::A_STAGE, &tmB, t.b_col + kt * G_BK, t.b_row, b, &full[s]);
+  };
+  if (tid == 0) {
+    for (int kt = 0; kt < Cfg::STAGES - 1 && kt < nkt; ++kt) issue(kt);
+  }
+  const int warp_m = warp & 3, warp_n = warp >> 2;
   const int g = lane >> 2, q = lane & 3;
-  double* Cp = C.p + b * C.stride + (long long)t.c_row * C.ld + t.c_col;
-  double* CTp = (t.flags & GT_STORE_T) ? CT.p + b * CT.stride + (long long)t.ct_row * CT.ld + t.ct_col : nullptr;
+  double acc[Cfg::MF][Cfg::NF][2];
 #pragma unroll
-  for (int i = 0; i < GemmCfg::MF; ++i) {
-    const int r = warp_m * GemmCfg::WM + i * 8 + g;
-    if (r >= t.m) continue;
+  for (int i = 0; i < Cfg::MF; ++i)
 #pragma unroll
-    for (int j = 0; j < GemmCfg::NF; ++j) {
-      const int c = warp_n * GemmCfg::WN + j * 8 + 2 * q;
-      if (c >= t.n) continue;
-      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-      const bool two = (c + 1 < t.n);
-      double* dst = Cp + (long long)r * C.ld + c;
-      if (t.flags & GT_ACCUM) {
-        if (two) {
-          const double2 old = *reinterpret_cast<const double2*>(dst);
-          v0 += old.x;
-          v1 += old.y;
-        } else {
-          v0 += dst[0];
+    for (int j = 0; j < Cfg::NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int s = kt % Cfg::STAGES;
+    mbar_wait(&full[s], (kt / Cfg::STAGES) & 1);
+    if (lane == 0 && warp == (kt & (G_CW - 1)) && kt + Cfg::STAGES - 1 < nkt) issue(kt + Cfg::STAGES - 1);
+    __syncwarp();
+    const double* As = pipe + (size_t)s * Cfg::STAGE;
+    const double* a_base = As + (warp_m * Cfg::WM + g) * G_LDS + q;
+    const double* b_base = As + Cfg::A_STAGE + (warp_n * Cfg::WN + g) * G_LDS + q;
+    const int k0 = kt * G_BK;
+    bool masked = false;
+    if (t.a_tri == 1) masked |= (k0 + G_BK - 1 > t.a_lim0);
+    if (t.b_tri == 1) masked |= (k0 + G_BK - 1 > t.b_lim0);
+    if (t.b_tri == 2) masked |= (k0 < t.b_lim0 + Cfg::BN - 1);
+#pragma unroll
+    for (int kk = 0; kk < G_BK / 4; ++kk) {
+      double a[Cfg::MF], bf[Cfg::NF];
+#pragma unroll
+      for (int i = 0; i < Cfg::MF; ++i) a[i] = a_base[i * 8 * G_LDS + kk * 4];
+#pragma unroll
+      for (int j = 0; j < Cfg::NF; ++j) bf[j] = b_base[j * 8 * G_LDS + kk * 4];
+      if (masked) {
+        const int k = k0 + kk * 4 + q;
+        if (t.a_tri == 1) {
+#pragma unroll
+          for (int i = 0; i < Cfg::MF; ++i)
+            if (k > t.a_lim0 + warp_m * Cfg::WM + i * 8 + g) a[i] = 0.0;
+        }
+        if (t.b_tri == 1) {
+#pragma unroll
+          for (int j = 0; j < Cfg::NF; ++j)
+            if (k > t.b_lim0 + warp_n * Cfg::WN + j * 8 + g) bf[j] = 0.0;
+        } else if (t.b_tri == 2) {
+#pragma unroll
+          for (int j = 0; j < Cfg::NF; ++j)
+            if (k < t.b_lim0 + warp_n * Cfg::WN + j * 8 + g) bf[j] = 0.0;
         }
       }
-      if (t.flags & GT_STORE) {
-        if (two) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-        else dst[0] = v0;
+#pragma unroll
+      for (int i = 0; i < Cfg::MF; ++i)
+#pragma unroll
+        for (int j = 0; j < Cfg::NF; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  // ---- epilogue: C = / += alpha * acc, optional transposed store.  The C reads of one fragment row are issued
+  //      together (NF loads in flight) before they are consumed. ----
+  double* Cp = C.p + (long long)b * C.stride + (long long)t.c_row * C.ld + t.c_col;
+  double* CTp = (t.flags & GT_STORE_T) ? CT.p + (long long)b * CT.stride + (long long)t.ct_row * CT.ld + t.ct_col : nullptr;
+  const bool accum = (t.flags & GT_ACCUM) != 0, store = (t.flags & GT_STORE) != 0;
+#pragma unroll
+  for (int i = 0; i < Cfg::MF; ++i) {
+    const int r = warp_m * Cfg::WM + i * 8 + g;
+    if (r >= t.m) continue;
+    double* crow = Cp + (long long)r * C.ld;
+    double2 old[Cfg::NF];
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) {
+      const int c = warp_n * Cfg::WN + j * 8 + 2 * q;
+      old[j] = make_double2(0.0, 0.0);
+      if (accum && c < t.n) {
+        if (c + 1 < t.n) old[j] = *reinterpret_cast<const double2*>(crow + c);
+        else old[j].x = crow[c];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < Cfg::NF; ++j) {
+      const int c = warp_n * Cfg::WN + j * 8 + 2 * q;
+      if (c >= t.n) continue;
+      const double v0 = fma(alpha, acc[i][j][0], old[j].x), v1 = fma(alpha, acc[i][j][1], old[j].y);
+      const bool two = (c + 1 < t.n);
+      if (store) {
+        if (two) *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);
+        else crow[c] = v0;
       }
       if (CTp) {
         CTp[(long long)c * CT.ld + r] = v0;
@@ -68,79 +160,147 @@ gemm_tasks_kernel(const GemmTask* __restrict__ tasks, MatView A, MatView B, MatV
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Diagonal block: factor the bs x bs lower block in shared memory (one thread per row, left-looking by
-// columns), write it back, invert the factor, and publish the inverse.
+// Diagonal block: factor the bs x bs lower block (bs <= 64), write it back, invert the factor, publish the inverse.
+// 256 threads.  Cholesky: right-looking with the block held in registers (thread (ti, tk) owns the 4 x 4 tile at
+// rows 4ti.., cols 4tk..); per column the owners publish the raw column, ONE barrier, every thread applies the
+// rank-1 update to its tile.  Inverse: row sweep, 4 lanes per column of X with a shuffle reduction.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB, 1)
+constexpr int DIAG_THREADS = 256;
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nblk, MatView linv, int has_linv,
                    int* __restrict__ status) {
   extern __shared__ __align__(16) double diag_smem[];
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem);
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem + NB * (NB + 1));
+  __shared__ double colbuf[2][NB];
+  __shared__ double dvec[NB];
   __shared__ int bad;
-  const int b = blockIdx.x, i = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x;
   const int r0 = blk * NB, bs = min(NB, n - r0);
   double* Lp = L.p + (long long)b * L.stride + (long long)r0 * L.ld + r0;
-  if (i == 0) bad = 0;
-  // load the lower block (thread i loads row i)
-  for (int c = 0; c < NB; ++c) {
-    // coalesce over columns: thread i reads column i of row c
-    double v = 0.0;
-    if (c < bs && i < bs && i <= c) v = Lp[(long long)c * L.ld + i];
-    Ls[c][i] = v;
+  if (tid == 0) bad = 0;
+  // load the lower block, identity-padded beyond bs so that the padded factor is the identity there
+  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
+    const int r = e / NB, c = e % NB;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < bs && c <= r) v = Lp[(long long)r * L.ld + c];
+    Ls[r][c] = v;
   }
   __syncthreads();
-  // left-looking column Cholesky: thread i owns row i
-  for (int j = 0; j < bs; ++j) {
-    double s0 = 0.0, s1 = 0.0;
-    if (i >= j && i < bs) {
-      int k = 0;
-      for (; k + 1 < j; k += 2) {
-        s0 = fma(Ls[i][k], Ls[j][k], s0);
-        s1 = fma(Ls[i][k + 1], Ls[j][k + 1], s1);
+  const int ti = tid >> 4, tk = tid & 15;
+  const bool active = ti >= tk;
+  double a[4][4];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) a[ii][kk] = active ? Ls[4 * ti + ii][4 * tk + kk] : 0.0;
+#pragma unroll 1
+  for (int jb = 0; jb < NB / 4; ++jb) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * jb + jj;
+      double* cb = colbuf[j & 1];
+      if (tk == jb && active) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) cb[4 * ti + ii] = a[ii][jj];
       }
-      if (k < j) s0 = fma(Ls[i][k], Ls[j][k], s0);
-    }
-    const double s = (i >= j && i < bs) ? Ls[i][j] - (s0 + s1) : 0.0;
-    __syncthreads();
-    if (i == j) {
-      if (!(s > 0.0)) {
-        if (bad == 0) bad = r0 + j + 1;
-        Ls[j][j] = nan("");
-      } else {
-        Ls[j][j] = sqrt(s);
+      __syncthreads();
+      const double d = cb[j];
+      if (tid == 0) {
+        dvec[j] = d;
+        if (!(d > 0.0) && bad == 0) bad = r0 + j + 1;
       }
-    }
-    __syncthreads();
-    if (i > j && i < bs) Ls[i][j] = s / Ls[j][j];
-    __syncthreads();
-  }
-  if (i == 0 && bad) atomicCAS(&status[b], 0, bad);
-  // write the factor back (coalesced over columns)
-  for (int c = 0; c < bs; ++c)
-    if (i <= c && i < bs) Lp[(long long)c * L.ld + i] = Ls[c][i];
-  // inverse: thread c solves L x = e_c (column c of the inverse), rows in sequence
-  for (int r = 0; r < NB; ++r) Xs[r][i] = 0.0;
-  if (i < bs) {
-    for (int r = i; r < bs; ++r) {
-      double s0 = (r == i) ? 1.0 : 0.0, s1 = 0.0;
-      int k = i;
-      for (; k + 1 < r; k += 2) {
-        s0 = fma(-Ls[r][k], Xs[k][i], s0);
-        s1 = fma(-Ls[r][k + 1], Xs[k + 1][i], s1);
+      if (active && 4 * ti + 3 > j && 4 * tk + 3 > j) {
+        const double inv = 1.0 / d;
+        double ci[4], ck[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) ci[ii] = cb[4 * ti + ii];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) ck[kk] = cb[4 * tk + kk] * inv;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (4 * tk + kk > j) a[ii][kk] = fma(-ci[ii], ck[kk], a[ii][kk]);
       }
-      if (k < r) s0 = fma(-Ls[r][k], Xs[k][i], s0);
-      Xs[r][i] = (s0 + s1) / Ls[r][r];
     }
   }
   __syncthreads();
-  // publish: dinv block [NB x NB] row-major with explicit zeros above the diagonal / beyond bs
+  // L[i][k] = raw column value / sqrt(pivot)
+  if (active) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = 4 * tk + kk;
+      const double piv = dvec[k];
+      const double sq = (piv > 0.0) ? sqrt(piv) : nan("");
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = 4 * ti + ii;
+        if (i == k) Ls[i][k] = sq;
+        else if (i > k) Ls[i][k] = a[ii][kk] / sq;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && bad) atomicCAS(&status[b], 0, bad);
+  for (int e = tid; e < bs * NB; e += DIAG_THREADS) {
+    const int r = e / NB, c = e % NB;
+    if (c <= r) Lp[(long long)r * L.ld + c] = Ls[r][c];
+  }
+  // ---- inverse X = L^-1, blocked: 16 x 16 diagonal blocks by forward substitution (one thread per column), then
+  //      X21 = -X22 (L21 X11) for the two 32-blocks and for the 64-block (small dense products, all threads) ----
+  __shared__ double rdiag[NB];
+  __shared__ double Ts[32][33];
+  for (int e = tid; e < NB * (NB + 1); e += DIAG_THREADS) (&Xs[0][0])[e] = 0.0;
+  if (tid < NB) rdiag[tid] = 1.0 / Ls[tid][tid];
+  __syncthreads();
+  if (tid < NB) {
+    const int d0 = (tid >> 4) * 16, c = tid & 15;
+    double x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double s0 = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) s0 = fma(-Ls[d0 + r][d0 + k], (k >= c) ? x[k] : 0.0, s0);
+      x[r] = (r >= c) ? s0 * rdiag[d0 + r] : 0.0;
+      Xs[d0 + r][d0 + c] = x[r];
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int s16 = 16; s16 <= 32; s16 *= 2) {
+    // pairs (b1 = 2 s16 p, b2 = b1 + s16); T = L21 X11 (k >= nn), then X21 = -X22 T (k <= m)
+    const int npair = NB / (2 * s16), per = s16 * s16;
+    for (int e = tid; e < npair * per; e += DIAG_THREADS) {
+      const int p = e / per, m = (e % per) / s16, nn = e % s16;
+      const int b1 = 2 * s16 * p, b2 = b1 + s16;
+      double acc = 0.0;
+      for (int k = nn; k < s16; ++k) acc = fma(Ls[b2 + m][b1 + k], Xs[b1 + k][b1 + nn], acc);
+      Ts[p * s16 + m][nn] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < npair * per; e += DIAG_THREADS) {
+      const int p = e / per, m = (e % per) / s16, nn = e % s16;
+      const int b1 = 2 * s16 * p, b2 = b1 + s16;
+      double acc = 0.0;
+      for (int k = 0; k <= m; ++k) acc = fma(Xs[b2 + m][b2 + k], Ts[p * s16 + k][nn], acc);
+      Xs[b2 + m][b1 + nn] = -acc;
+    }
+    __syncthreads();
+  }
+  // publish: dinv block [NB x NB] row-major with explicit zeros above the diagonal / outside bs
   double* dp = dinv + ((long long)b * nblk + blk) * (NB * NB);
-  for (int r = 0; r < NB; ++r) dp[r * NB + i] = Xs[r][i];
+  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
+    const int r = e / NB, cc = e % NB;
+    dp[e] = (r < bs && cc < bs) ? Xs[r][cc] : 0.0;
+  }
   if (has_linv) {
     double* ip = linv.p + (long long)b * linv.stride + (long long)r0 * linv.ld + r0;
-    for (int r = 0; r < bs; ++r)
-      if (i < bs) ip[(long long)r * linv.ld + i] = (i <= r) ? Xs[r][i] : Xs[i][r];
+    for (int e = tid; e < bs * NB; e += DIAG_THREADS) {
+      const int r = e / NB, cc = e % NB;
+      if (cc < bs) ip[(long long)r * linv.ld + cc] = (cc <= r) ? Xs[r][cc] : Xs[cc][r];
+    }
   }
 }
 
@@ -202,44 +362,83 @@ static GemmTask blank_task() {
   return t;
 }
 
-int plan_build(LinalgPlan& plan, int n, int extra_rows) {
+static void shape_dims(int shape, int& tm, int& tn) {
+  tm = (shape == 2) ? 64 : 128;
+  tn = (shape == 0) ? 128 : 64;
+}
+
+int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   plan_free(plan);
   plan.n = n;
   plan.rows = n + extra_rows;
   plan.nblk = ceil_div(n, NB);
+  // tile shapes: a single matrix needs many small CTAs on the latency-critical 64-wide steps; batches fill the
+  // machine with 128 x 64 tiles everywhere
+  plan.shape_panel = single ? 2 : 1;
+  plan.shape_inner = single ? 2 : 1;
+  plan.shape_outer = 1;
   std::vector<GemmTask> tasks;
-  const int T = GemmCfg::BM;   // 128
+  const int T = 128;   // tile edge of the triangular-inverse products (shape L)
   plan.panel.resize(plan.nblk);
   plan.trail.resize(plan.nblk);
-  for (int j = 0; j < plan.nblk; ++j) {
-    const int c0 = j * NB, bs = std::min(NB, n - c0), r_begin = c0 + bs;
-    // panel: rows below the diagonal block (including appended rows): L_ij = A_ij * Dinv_j^T
-    plan.panel[j].begin = (int)tasks.size();
-    for (int r = r_begin; r < plan.rows; r += T) {
-      GemmTask t = blank_task();
-      t.a_row = r; t.a_col = c0;
-      t.b_row = j * NB; t.b_col = 0;          // in the dinv view (ld = NB)
-      t.c_row = r; t.c_col = c0;
-      t.m = std::min(T, plan.rows - r); t.n = bs; t.k = bs;
-      t.flags = GT_STORE;
-      tasks.push_back(t);
-    }
-    plan.panel[j].count = (int)tasks.size() - plan.panel[j].begin;
-    // trailing update: C[I][K] -= L[I][c0:c0+bs] * L[K][c0:c0+bs]^T for the lower triangle of the rest
-    plan.trail[j].begin = (int)tasks.size();
-    for (int r = r_begin; r < plan.rows; r += T) {
-      const int m = std::min(T, plan.rows - r);
-      for (int c = r_begin; c < n && c <= r + m - 1; c += T) {
+  plan.outer.clear();
+  int pm, pn, im, in_, om, on;
+  shape_dims(plan.shape_panel, pm, pn);
+  shape_dims(plan.shape_inner, im, in_);
+  shape_dims(plan.shape_outer, om, on);
+  (void)pn;
+  // Right-looking with two block sizes: inside an outer block of OUTER_W columns the 64-wide steps update only the
+  // rest of that outer block (K = 64, few tiles); the matrix to the right is updated once per outer block with
+  // K = OUTER_W, where the tensor pipe runs long k loops and every C tile is read and written once per 256 columns.
+  for (int J0 = 0; J0 < n; J0 += OUTER_W) {
+    const int J1 = std::min(J0 + OUTER_W, n);
+    for (int c0 = J0; c0 < J1; c0 += NB) {
+      const int j = c0 / NB, bs = std::min(NB, n - c0), r_begin = c0 + bs;
+      // panel: rows below the diagonal block (including appended rows): L_ij = A_ij * Dinv_j^T
+      plan.panel[j].begin = (int)tasks.size();
+      for (int r = r_begin; r < plan.rows; r += pm) {
         GemmTask t = blank_task();
         t.a_row = r; t.a_col = c0;
-        t.b_row = c; t.b_col = c0;
+        t.b_row = j * NB; t.b_col = 0;          // in the dinv view (ld = NB)
+        t.c_row = r; t.c_col = c0;
+        t.m = std::min(pm, plan.rows - r); t.n = bs; t.k = bs;
+        t.flags = GT_STORE;
+        tasks.push_back(t);
+      }
+      plan.panel[j].count = (int)tasks.size() - plan.panel[j].begin;
+      // inner trailing update: columns of this outer block to the right of block j
+      plan.trail[j].begin = (int)tasks.size();
+      for (int r = r_begin; r < plan.rows; r += im) {
+        const int m = std::min(im, plan.rows - r);
+        for (int c = r_begin; c < J1 && c <= r + m - 1; c += in_) {
+          GemmTask t = blank_task();
+          t.a_row = r; t.a_col = c0;
+          t.b_row = c; t.b_col = c0;
+          t.c_row = r; t.c_col = c;
+          t.m = m; t.n = std::min(in_, J1 - c); t.k = bs;
+          t.flags = GT_ACCUM | GT_STORE;
+          tasks.push_back(t);
+        }
+      }
+      plan.trail[j].count = (int)tasks.size() - plan.trail[j].begin;
+    }
+    // outer trailing update: C[I][K] -= L[I][J0:J1] * L[K][J0:J1]^T for the lower triangle right of the outer block
+    ChunkRange o;
+    o.begin = (int)tasks.size();
+    for (int r = J1; r < plan.rows; r += om) {
+      const int m = std::min(om, plan.rows - r);
+      for (int c = J1; c < n && c <= r + m - 1; c += on) {
+        GemmTask t = blank_task();
+        t.a_row = r; t.a_col = J0;
+        t.b_row = c; t.b_col = J0;
         t.c_row = r; t.c_col = c;
-        t.m = m; t.n = std::min(T, n - c); t.k = bs;
+        t.m = m; t.n = std::min(on, n - c); t.k = J1 - J0;
         t.flags = GT_ACCUM | GT_STORE;
         tasks.push_back(t);
       }
     }
-    plan.trail[j].count = (int)tasks.size() - plan.trail[j].begin;
+    o.count = (int)tasks.size() - o.begin;
+    plan.outer.push_back(o);
   }
   // triangular inverse levels: s = NB, 2NB, ... ; pairs (block1 = [o, o+s), block2 = [o+s, min(o+2s, n)))
   for (int s = NB; s < n; s *= 2) {
@@ -295,28 +494,47 @@ void plan_free(LinalgPlan& plan) {
   plan = LinalgPlan();
 }
 
-static int launch_gemm_tasks(const GemmTask* tasks, int count, int batch, MatView A, MatView B, MatView C, MatView CT,
-                             double alpha, cudaStream_t st) {
+// A / B operands are described by (view, logical rows, logical cols): elements outside read as zero.
+struct Operand {
+  MatView v;
+  int rows, cols;
+};
+
+template <class Cfg>
+static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C, MatView CT,
+                           double alpha, cudaStream_t st) {
   if (count <= 0 || batch <= 0) return SPW_OK;
   static bool attr_set[64] = {false};
   int dev = 0;
   SPW_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    SPW_CUDA(cudaFuncSetAttribute(gemm_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)GemmCfg::PIPE_BYTES));
+    SPW_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set[dev & 63] = true;
   }
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = std::min(65535, batch - b0);
-    MatView a = A, b = B, c = C, ct = CT;
-    a.p += (long long)b0 * A.stride;
-    b.p += (long long)b0 * B.stride;
-    c.p += (long long)b0 * C.stride;
+    MatView a = A.v, b = B.v, c = C, ct = CT;
+    a.p += (long long)b0 * A.v.stride;
+    b.p += (long long)b0 * B.v.stride;
+    if (c.p) c.p += (long long)b0 * C.stride;
     if (ct.p) ct.p += (long long)b0 * CT.stride;
-    gemm_tasks_kernel<<<dim3(count, nb), GemmCfg::NTHREADS, GemmCfg::PIPE_BYTES, st>>>(tasks, a, b, c, ct, alpha);
+    CUtensorMap tmA, tmB;
+    SPW_TRY(make_tensor_map(&tmA, a, A.cols, A.rows, nb, G_LDS, Cfg::BM));
+    SPW_TRY(make_tensor_map(&tmB, b, B.cols, B.rows, nb, G_LDS, Cfg::BN));
+    gemm_tma_kernel<Cfg><<<dim3(count, nb), G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tasks, c, ct, alpha);
     SPW_LAUNCHED();
   }
   return SPW_OK;
+}
+
+// shape: 0 = L (128 x 128), 1 = M (128 x 64), 2 = S (64 x 64); the task list must have been tiled accordingly
+static int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
+                             MatView CT, double alpha, cudaStream_t st) {
+  switch (shape) {
+    case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st);
+    case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st);
+    default: return launch_gemm_cfg<GCfgS>(tasks, count, batch, A, B, C, CT, alpha, st);
+  }
 }
 
 int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv, int batch, int* status,
@@ -324,6 +542,7 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
   MatView dv{dinv, NB, (long long)plan.nblk * NB * NB};
   MatView none{nullptr, 0, 0};
   MatView lv = linv ? *linv : none;
+  Operand opL{L, plan.rows, plan.n}, opD{dv, plan.nblk * NB, NB};
   constexpr size_t DIAG_SMEM = 2 * NB * (NB + 1) * sizeof(double);
   static bool diag_attr[64] = {false};
   int dev = 0;
@@ -332,20 +551,28 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     SPW_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     diag_attr[dev & 63] = true;
   }
+  const int per_outer = OUTER_W / NB;
   for (int j = 0; j < plan.nblk; ++j) {
-    diag_factor_kernel<<<batch, NB, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status);
+    diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status);
     SPW_LAUNCHED();
-    SPW_TRY(launch_gemm_tasks(plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, L, dv, L, none, 1.0, st));
-    SPW_TRY(launch_gemm_tasks(plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, L, L, L, none, -1.0, st));
+    SPW_TRY(launch_gemm_tasks(plan.shape_panel, plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, opL, opD,
+                              L, none, 1.0, st));
+    SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
+                              L, none, -1.0, st));
+    if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
+      const ChunkRange& o = plan.outer[j / per_outer];
+      SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
+    }
   }
   return SPW_OK;
 }
 
 int trtri_batched(const LinalgPlan& plan, MatView L, MatView linv, int batch, cudaStream_t st) {
   MatView none{nullptr, 0, 0};
+  Operand opL{L, plan.n, plan.n}, opI{linv, plan.n, plan.n};
   for (size_t lev = 0; lev < plan.inv1.size(); ++lev) {
-    SPW_TRY(launch_gemm_tasks(plan.d_tasks + plan.inv1[lev].begin, plan.inv1[lev].count, batch, L, linv, none, L, 1.0, st));
-    SPW_TRY(launch_gemm_tasks(plan.d_tasks + plan.inv2[lev].begin, plan.inv2[lev].count, batch, linv, L, linv, linv, -1.0, st));
+    SPW_TRY(launch_gemm_tasks(0, plan.d_tasks + plan.inv1[lev].begin, plan.inv1[lev].count, batch, opL, opI, none, L, 1.0, st));
+    SPW_TRY(launch_gemm_tasks(0, plan.d_tasks + plan.inv2[lev].begin, plan.inv2[lev].count, batch, opI, opL, linv, linv, -1.0, st));
   }
   return SPW_OK;
 }

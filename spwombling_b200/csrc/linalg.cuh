@@ -7,7 +7,8 @@
 
 namespace spw {
 
-constexpr int NB = 64;   // diagonal block size of the blocked Cholesky / triangular inverse
+constexpr int NB = 64;        // diagonal block size of the blocked Cholesky / triangular inverse
+constexpr int OUTER_W = 256;  // outer block width of the Cholesky (K of the big trailing updates)
 
 // One output tile of the task-driven NT GEMM kernel.
 struct GemmTask {
@@ -33,13 +34,16 @@ struct LinalgPlan {
   int n = 0;            // matrix order the plan was built for
   int rows = 0;         // rows actually factored (n, or n + 1 for the augmented hlm system)
   int nblk = 0;
-  std::vector<ChunkRange> panel, trail;         // per potrf step
+  int shape_panel = 1, shape_inner = 1, shape_outer = 1;   // GEMM tile shapes (0: 128x128, 1: 128x64, 2: 64x64)
+  std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
+  std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
   std::vector<ChunkRange> inv1, inv2;           // per trtri level
   GemmTask* d_tasks = nullptr;
   int n_tasks = 0;
 };
 
-int plan_build(LinalgPlan& plan, int n, int extra_rows);
+// single != 0: schedule for one matrix at a time (hlm chain): small tiles on the latency-critical steps
+int plan_build(LinalgPlan& plan, int n, int extra_rows, int single);
 void plan_free(LinalgPlan& plan);
 
 // Batched Cholesky of the leading n x n lower triangle of L (in place).  If extra_rows > 0 the rows
