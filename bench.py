@@ -267,7 +267,7 @@ def run_ours(args, w):
         traffic = json.load(open(tp)).get(args.workload)
     names = ["cov_assemble", "potrf", "trtri", "trmv", "cross_cov", "gradient_main"]
     phases = {nm: {"ms_per_step": ph_ms[i] / args.steps, "launch_groups": int(ph_calls[i])} for i, nm in enumerate(names)}
-    roofline = {"bound": "tensor", "kernel": "gradient_main_kernel (fused TRMM + Gram + 5x5 chol + draw)",
+    roofline = {"bound": "tensor", "kernel": "gradient_tma_kernel (TMA-fed fused TRMM + Gram + 5x5 chol + draw)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "peak_source": "measured FP64 tensor pipe (DMMA.8x8x4 micro-benchmark, profiles/FP64_PEAK.json; "

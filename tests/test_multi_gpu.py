@@ -1,0 +1,30 @@
+"""Multi-GPU checks (skipped unless >= 2 devices are visible): the in-process sharded entry point gives results
+bit-identical to one device (sharding by sample changes no arithmetic)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    import spwombling_b200 as spw
+    return spw.load().spw_device_count()
+
+
+def test_in_process_sharding_bit_identical():
+    import spwombling_b200 as spw
+    if _ndev() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rng = np.random.Generator(np.random.Philox(3))
+    n, S = 300, 11
+    coords = rng.random((n, 2))
+    gs = np.linspace(0.1, 0.9, 6)
+    grid = np.array([[a, b] for b in gs for a in gs])
+    model = {"phi": rng.uniform(15, 40, S), "sig2": rng.uniform(0.5, 2, S), "z": rng.standard_normal((S, n))}
+    eps = rng.standard_normal((S, grid.shape[0], 5))
+    one = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=3, eps=eps, ngpu=1, rounded=False)
+    for ngpu in range(2, min(_ndev(), 8) + 1):
+        many = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=3, eps=eps, ngpu=ngpu, rounded=False)
+        assert list(one) == list(many)
+        for k in one:
+            assert np.array_equal(one[k], many[k]), (ngpu, k)
