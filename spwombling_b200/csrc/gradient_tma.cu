@@ -73,7 +73,10 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int b = blockIdx.y;
   const int g0 = blockIdx.x * C::GPT;
   const int n = P.n;
-  const int nrb = (n + T_BM - 1) / T_BM;
+  // 128-row blocks aligned to the END of the matrix: block rb covers rows rb*128 - pad ... (+128); the ragged block
+  // is the first one (rows < 0 are outside the tensor: TMA zero-fills them), where the k range is shortest
+  const int pad = (T_BM - n % T_BM) % T_BM;
+  const int nrb = (n + pad) / T_BM;
 
   if (tid == 0) {
     for (int s = 0; s < T_STAGES; ++s) {
@@ -89,8 +92,8 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int f = 0;
       for (int rb = 0; rb < nrb; ++rb) {
-        const int r0 = rb * T_BM;
-        const int nkt = (min(r0 + T_BM, n) + T_BK - 1) / T_BK;
+        const int r0 = rb * T_BM - pad;
+        const int nkt = (r0 + T_BM + T_BK - 1) / T_BK;
         for (int kt = 0; kt < nkt; ++kt, ++f) {
           const int s = f % T_STAGES;
           const uint32_t ph = (f / T_STAGES) & 1;
@@ -104,7 +107,10 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== consumers: DMMA main loop + warp-local Gram epilogue =========================
-    const int warp_m = warp & 3, warp_n = warp >> 2;
+    // the two warps of an SM sub-partition (warp & 3) own row strips wm and 3 - wm, so the strips' unequal shares of
+    // the diagonal tiles (a strip skips the k tiles to the right of its last row) add up to the same work everywhere
+    const int warp_n = warp >> 2;
+    const int warp_m = warp_n ? (7 - warp) : warp;
     const int g = lane >> 2, q = lane & 3;
     double* stg = stg_all + (size_t)warp * 16 * C::LDG;
     const double* vvec = P.v + (long long)b * P.ldv;
@@ -141,8 +147,9 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     int f = 0;
     for (int rb = 0; rb < nrb; ++rb) {
-      const int r0 = rb * T_BM;
-      const int nkt = (min(r0 + T_BM, n) + T_BK - 1) / T_BK;
+      const int r0 = rb * T_BM - pad;
+      const int nkt = (r0 + T_BM + T_BK - 1) / T_BK;
+      const int strip0 = r0 + warp_m * 32;                 // first row of this warp's strip (may be < 0 in block 0)
       for (int kt = 0; kt < nkt; ++kt, ++f) {
         const int s = f % T_STAGES;
         const uint32_t ph = (f / T_STAGES) & 1;
@@ -152,8 +159,9 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const double* a_base = As + (warp_m * 32 + g) * T_LDS + q;
         const double* b_base = Bs + (warp_n * C::WN + g) * T_LDS + q;
         const int k0 = kt * T_BK;
-        const bool masked = (k0 + T_BK - 1 > r0);          // tile touches the diagonal: Linv's upper triangle holds
+        const bool masked = (k0 + T_BK - 1 > strip0);      // tile touches the diagonal: Linv's upper triangle holds
                                                            // the transposed copy, which must read as zero here
+        if (k0 <= strip0 + 31) {                           // else: the whole tile lies right of the strip's diagonal
 #pragma unroll
         for (int kk = 0; kk < T_BK / 4; ++kk) {
           double a[C::MF], bf[C::NF];
@@ -172,12 +180,13 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < C::NF; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
         }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
       }
       // ---- row block done: fold this warp's 32 x WN tile of W into its Gram / mean accumulators ----
-      const int rw = r0 + warp_m * 32 + lane;
-      const double vreg = (rw < n) ? vvec[rw] : 0.0;
+      const int rw = strip0 + lane;
+      const double vreg = (rw >= 0 && rw < n) ? vvec[rw] : 0.0;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         __syncwarp();
@@ -210,7 +219,7 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     double* Ms = pipe;                                               // [warp][NIT_W], aliases the (drained) ring
 #pragma unroll
     for (int t = 0; t < C::NACC; ++t)
-      if (live[t]) Ms[warp * C::NIT_W + lane + 32 * t] = gram[t];
+      if (live[t]) Ms[(warp_n * 4 + warp_m) * C::NIT_W + lane + 32 * t] = gram[t];
     asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMER_WARPS));
     if (tid < C::GPT && g0 + tid < P.g_count) {
       const int gl = tid;
