@@ -313,14 +313,14 @@ def run_ours(args, w):
 def bench_hlm(spw, args):
     """hlmBayes_sp iterations/s (BASELINE.json's second metric), N = 5000 matern2 and the README's N = 100."""
     out = {}
-    for n, niter in ((5000, 6), (100, 600)):
+    for n, niter in ((5000, 24), (100, 2000)):
         rng = np.random.Generator(np.random.Philox(2))
         coords = rng.random((n, 2))
         y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
         r6 = np.random.Generator(np.random.Philox(6))
         norm, unif = r6.standard_normal(3 * niter), r6.random(3 * niter)
         kw = dict(y=y, coords=coords, nburn=0, report=max(1, niter // 2), cov_type="matern2", verbose=False)
-        spw.hlmBayes_sp(niter=2, norm=norm, unif=unif, **kw)                     # warm-up (plans, attributes)
+        spw.hlmBayes_sp(niter=max(2, niter // 4), norm=norm, unif=unif, **kw)    # warm-up (plans, clocks)
         dt = 1e30
         for _ in range(3):                                                       # best of 3 (wall clock, host jitter)
             t0 = time.perf_counter()

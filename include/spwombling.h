@@ -54,6 +54,9 @@ long long spw_launch_count(int reset);
 int spw_profile_enable(int on);
 int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset);
 
+/* diagnostic: first call enables cycle counters in the diagonal-block kernel, later calls read them */
+int spw_debug_diag_timing(long long* out5);
+
 /* covariance kernels ----------------------------------------------------------------------------
  * spw_cov: as.matrix(dist(coords)) fused with cov_gaussian / cov_matern1 / cov_matern2
  *   replaces R/hlmBayes_sp.R:38 + R/cov_gaussian.R:14, R/cov_matern1.R:14, R/cov_matern2.R:14.

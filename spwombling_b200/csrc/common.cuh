@@ -63,6 +63,19 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// 1/sqrt(x) to full double precision on a short dependency chain: hardware approximation (2^-22) + two Newton
+// steps (the library rsqrt() costs ~250 cycles of latency, this ~100); non-positive / non-finite x give NaN or the
+// IEEE limits through the same formula, which the callers' pivot checks catch.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+  double e = fma(-(x * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-(x * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
+}
+
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 

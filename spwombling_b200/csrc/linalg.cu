@@ -162,100 +162,194 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ---------------------------------------------------------------------------------------------------
 // Diagonal block: factor the bs x bs lower block (bs <= 64), write it back, invert the factor, publish the inverse.
 // 256 threads.  Cholesky: right-looking with the block held in registers (thread (ti, tk) owns the 4 x 4 tile at
-// rows 4ti.., cols 4tk..); per column the owners publish the raw column, ONE barrier, every thread applies the
-// rank-1 update to its tile.  Inverse: row sweep, 4 lanes per column of X with a shuffle reduction.
+// rows 4ti.., cols 4tk..); the 64 pivots are taken four at a time: the owners of tile column jb publish their raw
+// tiles, ONE barrier, and every thread redundantly factors the 4 x 4 pivot tile, solves its own two 4 x 4
+// triangular systems and applies the rank-4 update to its tile (one barrier per 4 columns instead of per column).
+// Inverse: 16 x 16 diagonal blocks by forward substitution, then X21 = -X22 (L21 X11) for the 32- and 64-blocks as
+// small dense products (zeros above the diagonals make every loop a fixed-length, fully unrolled one).
 // ---------------------------------------------------------------------------------------------------
 constexpr int DIAG_THREADS = 256;
+long long* g_diag_dbg = nullptr;   // optional device buffer of 8 cycle counters (spw_debug_diag_timing)
+
+template <int S16>
+__device__ __forceinline__ void diag_inverse_level(double (*Ls)[NB + 1], double (*Xs)[NB + 1], double (*Ts)[33], int tid) {
+  // pairs (b1 = 2 S16 p, b2 = b1 + S16); each thread owns a 1 x 2 (S16 = 16) or 2 x 2 (S16 = 32) block of outputs
+  constexpr int MR = (S16 == 16) ? 1 : 2;
+  constexpr int TPP = (S16 / MR) * (S16 / 2);          // threads per pair: 128 (two pairs) or 256 (one pair)
+  const int p = tid / TPP, e = tid % TPP;
+  const int m0 = (e / (S16 / 2)) * MR, n0 = (e % (S16 / 2)) * 2;
+  const int b1 = 2 * S16 * p, b2 = b1 + S16;
+  double acc[MR][2];
+#pragma unroll
+  for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+  for (int k = 0; k < S16; ++k) {            // T = L21 X11   (X11 is lower triangular: zeros supply the k >= n bound)
+    const double x0 = Xs[b1 + k][b1 + n0], x1 = Xs[b1 + k][b1 + n0 + 1];
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      const double l = Ls[b2 + m0 + i][b1 + k];
+      acc[i][0] = fma(l, x0, acc[i][0]);
+      acc[i][1] = fma(l, x1, acc[i][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) {
+    Ts[p * S16 + m0 + i][n0] = acc[i][0];
+    Ts[p * S16 + m0 + i][n0 + 1] = acc[i][1];
+    acc[i][0] = acc[i][1] = 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < S16; ++k) {            // X21 = -X22 T   (X22 lower triangular: zeros supply the k <= m bound)
+    const double t0 = Ts[p * S16 + k][n0], t1 = Ts[p * S16 + k][n0 + 1];
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      const double x = Xs[b2 + m0 + i][b2 + k];
+      acc[i][0] = fma(x, t0, acc[i][0]);
+      acc[i][1] = fma(x, t1, acc[i][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) {
+    Xs[b2 + m0 + i][b1 + n0] = -acc[i][0];
+    Xs[b2 + m0 + i][b1 + n0 + 1] = -acc[i][1];
+  }
+  __syncthreads();
+}
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nblk, MatView linv, int has_linv,
-                   int* __restrict__ status) {
+                   int* __restrict__ status, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double diag_smem[];
+  long long t0 = 0;
+  if (dbg && threadIdx.x == 0 && blockIdx.x == 0) t0 = clock64();
+#define DIAG_MARK(i) if (dbg && threadIdx.x == 0 && blockIdx.x == 0) dbg[i] = clock64() - t0;
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem);
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem + NB * (NB + 1));
-  __shared__ double colbuf[2][NB];
-  __shared__ double dvec[NB];
+  __shared__ __align__(16) double Tb[2][16][16];      // published raw tiles of the current tile column
+  __shared__ double rdiag[NB];
+  __shared__ double Ts[32][33];
   __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int r0 = blk * NB, bs = min(NB, n - r0);
   double* Lp = L.p + (long long)b * L.stride + (long long)r0 * L.ld + r0;
   if (tid == 0) bad = 0;
-  // load the lower block, identity-padded beyond bs so that the padded factor is the identity there
-  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
-    const int r = e / NB, c = e % NB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < bs && c <= r) v = Lp[(long long)r * L.ld + c];
-    Ls[r][c] = v;
-  }
-  __syncthreads();
+  // ---- load: thread (ti, tk) reads its own 4 x 4 tile (identity-padded beyond bs) ----
   const int ti = tid >> 4, tk = tid & 15;
   const bool active = ti >= tk;
   double a[4][4];
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) a[ii][kk] = active ? Ls[4 * ti + ii][4 * tk + kk] : 0.0;
+    for (int kk = 0; kk < 4; ++kk) {
+      const int r = 4 * ti + ii, c = 4 * tk + kk;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (active && r < bs && c <= r) v = Lp[(long long)r * L.ld + c];
+      a[ii][kk] = v;
+    }
+  DIAG_MARK(0)
+  // ---- Cholesky, four pivots per barrier ----
 #pragma unroll 1
   for (int jb = 0; jb < NB / 4; ++jb) {
+    double (*T)[16] = Tb[jb & 1];
+    if (tk == jb && active) {
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = 4 * jb + jj;
-      double* cb = colbuf[j & 1];
-      if (tk == jb && active) {
+      for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) cb[4 * ti + ii] = a[ii][jj];
-      }
-      __syncthreads();
-      const double d = cb[j];
-      if (tid == 0) {
-        dvec[j] = d;
-        if (!(d > 0.0) && bad == 0) bad = r0 + j + 1;
-      }
-      if (active && 4 * ti + 3 > j && 4 * tk + 3 > j) {
-        const double inv = 1.0 / d;
-        double ci[4], ck[4];
+        for (int kk = 0; kk < 4; kk += 2)
+          *reinterpret_cast<double2*>(&T[ti][ii * 4 + kk]) = make_double2(a[ii][kk], a[ii][kk + 1]);
+    }
+    __syncthreads();
+    if (active && tk >= jb) {
+      const double* D = T[jb];
+      // 4 x 4 Cholesky of the pivot tile (lower part), with reciprocal square roots
+      const double q0 = D[0], rs0 = fast_rsqrt(q0);
+      const double l10 = D[4] * rs0, l20 = D[8] * rs0, l30 = D[12] * rs0;
+      const double q1 = fma(-l10, l10, D[5]), rs1 = fast_rsqrt(q1);
+      const double l21 = fma(-l20, l10, D[9]) * rs1, l31 = fma(-l30, l10, D[13]) * rs1;
+      const double q2 = fma(-l21, l21, fma(-l20, l20, D[10])), rs2 = fast_rsqrt(q2);
+      const double l32 = fma(-l31, l21, fma(-l30, l20, D[14])) * rs2;
+      const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[15]))), rs3 = fast_rsqrt(q3);
+      if (ti == jb) {                       // the diagonal tile itself: final factor entries (and the pivot check)
+        if (tk == jb) {
+          int first_bad = 0;
+          if (!(q3 > 0.0)) first_bad = 4;
+          if (!(q2 > 0.0)) first_bad = 3;
+          if (!(q1 > 0.0)) first_bad = 2;
+          if (!(q0 > 0.0)) first_bad = 1;
+          if (first_bad && bad == 0) bad = r0 + 4 * jb + first_bad;
+          a[0][0] = q0 * rs0;
+          a[1][0] = l10; a[1][1] = q1 * rs1;
+          a[2][0] = l20; a[2][1] = l21; a[2][2] = q2 * rs2;
+          a[3][0] = l30; a[3][1] = l31; a[3][2] = l32; a[3][3] = q3 * rs3;
+          a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
+        }
+      } else {
+        // Xi = Ci Ld^-T (rows of this thread's row tile), Xk = Ck Ld^-T (rows of its column tile)
+        double xi[4][4], xk[4][4];
+        const double* Ci = T[ti];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) ci[ii] = cb[4 * ti + ii];
+        for (int r = 0; r < 4; ++r) {
+          const double c0 = Ci[4 * r], c1 = Ci[4 * r + 1], c2 = Ci[4 * r + 2], c3 = Ci[4 * r + 3];
+          xi[r][0] = c0 * rs0;
+          xi[r][1] = fma(-xi[r][0], l10, c1) * rs1;
+          xi[r][2] = fma(-xi[r][1], l21, fma(-xi[r][0], l20, c2)) * rs2;
+          xi[r][3] = fma(-xi[r][2], l32, fma(-xi[r][1], l31, fma(-xi[r][0], l30, c3))) * rs3;
+        }
+        if (tk == jb) {                     // column owner below the diagonal: these are its final factor entries
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) ck[kk] = cb[4 * tk + kk] * inv;
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
+            for (int c = 0; c < 4; ++c) a[r][c] = xi[r][c];
+        } else {
+          if (tk == ti) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            if (4 * tk + kk > j) a[ii][kk] = fma(-ci[ii], ck[kk], a[ii][kk]);
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) xk[r][c] = xi[r][c];
+          } else {
+            const double* Ck = T[tk];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const double c0 = Ck[4 * r], c1 = Ck[4 * r + 1], c2 = Ck[4 * r + 2], c3 = Ck[4 * r + 3];
+              xk[r][0] = c0 * rs0;
+              xk[r][1] = fma(-xk[r][0], l10, c1) * rs1;
+              xk[r][2] = fma(-xk[r][1], l21, fma(-xk[r][0], l20, c2)) * rs2;
+              xk[r][3] = fma(-xk[r][2], l32, fma(-xk[r][1], l31, fma(-xk[r][0], l30, c3))) * rs3;
+            }
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              double s = a[ii][kk];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) s = fma(-xi[ii][c], xk[kk][c], s);
+              a[ii][kk] = s;
+            }
+        }
       }
     }
   }
-  __syncthreads();
-  // L[i][k] = raw column value / sqrt(pivot)
-  if (active) {
+  DIAG_MARK(1)
+  // ---- factor -> shared memory (zeros above the diagonal) and back to global ----
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const int k = 4 * tk + kk;
-      const double piv = dvec[k];
-      const double sq = (piv > 0.0) ? sqrt(piv) : nan("");
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii) {
-        const int i = 4 * ti + ii;
-        if (i == k) Ls[i][k] = sq;
-        else if (i > k) Ls[i][k] = a[ii][kk] / sq;
-      }
+      const int r = 4 * ti + ii, c = 4 * tk + kk;
+      const double v = (active && c <= r) ? a[ii][kk] : 0.0;
+      Ls[r][c] = v;
+      Xs[r][c] = 0.0;
+      if (active && c <= r && r < bs) Lp[(long long)r * L.ld + c] = v;
     }
-  }
   __syncthreads();
   if (tid == 0 && bad) atomicCAS(&status[b], 0, bad);
-  for (int e = tid; e < bs * NB; e += DIAG_THREADS) {
-    const int r = e / NB, c = e % NB;
-    if (c <= r) Lp[(long long)r * L.ld + c] = Ls[r][c];
-  }
-  // ---- inverse X = L^-1, blocked: 16 x 16 diagonal blocks by forward substitution (one thread per column), then
-  //      X21 = -X22 (L21 X11) for the two 32-blocks and for the 64-block (small dense products, all threads) ----
-  __shared__ double rdiag[NB];
-  __shared__ double Ts[32][33];
-  for (int e = tid; e < NB * (NB + 1); e += DIAG_THREADS) (&Xs[0][0])[e] = 0.0;
+  DIAG_MARK(2)
+  // ---- inverse X = L^-1 ----
   if (tid < NB) rdiag[tid] = 1.0 / Ls[tid][tid];
   __syncthreads();
-  if (tid < NB) {
+  if (tid < NB) {                           // 16 x 16 diagonal blocks: one thread per column, forward substitution
     const int d0 = (tid >> 4) * 16, c = tid & 15;
     double x[16];
 #pragma unroll
@@ -268,27 +362,9 @@ diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nbl
     }
   }
   __syncthreads();
-#pragma unroll 1
-  for (int s16 = 16; s16 <= 32; s16 *= 2) {
-    // pairs (b1 = 2 s16 p, b2 = b1 + s16); T = L21 X11 (k >= nn), then X21 = -X22 T (k <= m)
-    const int npair = NB / (2 * s16), per = s16 * s16;
-    for (int e = tid; e < npair * per; e += DIAG_THREADS) {
-      const int p = e / per, m = (e % per) / s16, nn = e % s16;
-      const int b1 = 2 * s16 * p, b2 = b1 + s16;
-      double acc = 0.0;
-      for (int k = nn; k < s16; ++k) acc = fma(Ls[b2 + m][b1 + k], Xs[b1 + k][b1 + nn], acc);
-      Ts[p * s16 + m][nn] = acc;
-    }
-    __syncthreads();
-    for (int e = tid; e < npair * per; e += DIAG_THREADS) {
-      const int p = e / per, m = (e % per) / s16, nn = e % s16;
-      const int b1 = 2 * s16 * p, b2 = b1 + s16;
-      double acc = 0.0;
-      for (int k = 0; k <= m; ++k) acc = fma(Xs[b2 + m][b2 + k], Ts[p * s16 + k][nn], acc);
-      Xs[b2 + m][b1 + nn] = -acc;
-    }
-    __syncthreads();
-  }
+  diag_inverse_level<16>(Ls, Xs, Ts, tid);
+  diag_inverse_level<32>(Ls, Xs, Ts, tid);
+  DIAG_MARK(3)
   // publish: dinv block [NB x NB] row-major with explicit zeros above the diagonal / outside bs
   double* dp = dinv + ((long long)b * nblk + blk) * (NB * NB);
   for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
@@ -302,6 +378,8 @@ diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nbl
       if (cc < bs) ip[(long long)r * linv.ld + cc] = (cc <= r) ? Xs[r][cc] : Xs[cc][r];
     }
   }
+  DIAG_MARK(4)
+#undef DIAG_MARK
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -553,7 +631,8 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
   }
   const int per_outer = OUTER_W / NB;
   for (int j = 0; j < plan.nblk; ++j) {
-    diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status);
+    diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
+                                                               g_diag_dbg);
     SPW_LAUNCHED();
     SPW_TRY(launch_gemm_tasks(plan.shape_panel, plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, opL, opD,
                               L, none, 1.0, st));

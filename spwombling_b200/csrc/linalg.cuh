@@ -43,6 +43,7 @@ struct LinalgPlan {
 };
 
 // single != 0: schedule for one matrix at a time (hlm chain): small tiles on the latency-critical steps
+extern long long* g_diag_dbg;
 int plan_build(LinalgPlan& plan, int n, int extra_rows, int single);
 void plan_free(LinalgPlan& plan);
 

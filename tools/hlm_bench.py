@@ -1,4 +1,4 @@
-"""hlmBayes_sp timing helper: python tools/hlm_bench.py N NITER [cov_type]  (prints iterations/s)."""
+"""hlmBayes_sp timing helper: python tools/hlm_bench.py N NITER [cov_type]  (prints iterations/s per repetition)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,6 +7,7 @@ import spwombling_b200 as spw
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 niter = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 cov = sys.argv[3] if len(sys.argv) > 3 else "matern2"
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 rng = np.random.Generator(np.random.Philox(2))
 coords = rng.random((n, 2))
 y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
@@ -14,7 +15,7 @@ r6 = np.random.Generator(np.random.Philox(6))
 norm, unif = r6.standard_normal(3 * niter), r6.random(3 * niter)
 kw = dict(y=y, coords=coords, nburn=0, report=max(1, niter // 2), cov_type=cov, verbose=False)
 spw.hlmBayes_sp(niter=2, norm=norm, unif=unif, **kw)
-for rep in range(3):
+for rep in range(reps):
     spw.launch_count(reset=True)
     t0 = time.perf_counter()
     out = spw.hlmBayes_sp(niter=niter, norm=norm, unif=unif, **kw)
