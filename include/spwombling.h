@@ -126,6 +126,15 @@ int spw_gradient_shard_dev(int type, int n, const double* coords_dev, int g, con
                            double* out_draws_dev, double* out_mean_dev, double* out_var_dev,
                            int* info, void* stream);
 
+/* spsample (the producer of model$z between the two hot paths) --------------------
+ * spw_spsample_run: the per-sample Gibbs draw of the latent process, R/spsample_beta.R:50-100, without the p x p
+ *   regression block (:76-78), which the host evaluates: w [n x S] column-major holds (y - X beta_s)/tau2_s,
+ *   eps [n x S] the rnorm(N) of :93.  out_z [S x n] column-major (z.mcmc).  bad[s] != 0 marks a "Bad Iteration"
+ *   (:85: chol(Sig.Z.in) failed); the host applies the fallback rule of :86-89 to those rows.  A sample whose
+ *   chol(R.Z) fails is redone with R.Z + 1e-4 I (:70-71). */
+int spw_spsample_run(int type, int n, const double* coords, int S, const double* phi, const double* sig2,
+                     const double* tau2, const double* w, const double* eps, double* out_z, int* bad, int* info);
+
 /* spw_hpd_summary: batch medians, median of batch medians and coda::HPDinterval over the batch
  *   medians -- R/spatial_gradient.R:391-419 (:353-358 for matern1).  draws [S x g] column-major,
  *   out [g x 3] column-major (estimate, lower, upper), unrounded. */
@@ -141,6 +150,15 @@ int spw_cov_p(const int* type, const int* n, const double* coords, const double*
               double* out, int* status);
 int spw_hpd_summary_p(const int* S, const int* g, const int* nbatch, const double* prob,
                       const double* draws, double* out, int* status);
+/* hyper = c(a.sigma, b.sigma, a.tau, b.tau, lower.phi, upper.phi) */
+int spw_hlm_run_p(const int* n, const double* coords, const double* y, const int* type, const int* niter,
+                  const int* nburn, const int* report, const double* hyper, const double* norm, const double* unif,
+                  const int* want_trgt, double* out_sig2, double* out_tau2, double* out_phi, double* out_trgt,
+                  double* out_accept, double* out_tuning, int* info, int* status);
+int spw_gradient_run_p(const int* type, const int* n, const double* coords, const int* g, const double* grid,
+                       const int* S, const double* phi, const double* sig2, const double* z, const double* eps,
+                       const int* ngpu, const int* nbatch, const double* prob, const int* want_draws,
+                       double* out_draws, double* out_summary, int* info, int* status);
 
 #ifdef __cplusplus
 }

@@ -40,11 +40,14 @@ SIGNATURES = {
                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spw_gradient_shard_dev": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
                                        c_vp, c_vp, c_vp, c_vp]),
+    "spw_spsample_run": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spw_hpd_summary": (c_int, [c_int, c_int, c_int, c_dbl, c_vp, c_vp]),
     "spw_hpd_summary_dev": (c_int, [c_int, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
     "spw_draws_to_r_layout_dev": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "spw_cov_p": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spw_hpd_summary_p": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "spw_hlm_run_p": (c_int, [c_vp] * 19),
+    "spw_gradient_run_p": (c_int, [c_vp] * 18),
 }
 
 _lib = None

@@ -217,6 +217,63 @@ def spatial_gradient(coords=None, model=None, cov_type=None, grid_points=None, n
     return out
 
 
+# ---- spsample ------------------------------------------------------------------------
+def spsample(y=None, X=None, coords=None, phi=None, sig2=None, tau2=None, cov_type=None, silent=True,
+             eps_beta=None, eps_z=None, rng=None):
+    """Posterior samples of the latent process z (and intercept / regression coefficients) given the
+    (phi, sig2, tau2) draws -- R/spsample_beta.R:19-113.  Returns ``{"z": S x N, "beta0": S, "beta": S x p}``
+    (the reference ``unlist``s beta into a vector, :108).  The N x N work (three Cholesky factorisations and two
+    inverses per sample, :70-93) runs on the GPU; the p x p regression block (:76-78) is evaluated here on the host.
+    ``eps_beta`` [S, p] / ``eps_z`` [S, N] inject the ``rnorm(ncol(X))`` / ``rnorm(N)`` variates of :78 / :93.
+    """
+    if cov_type is None:
+        raise ValueError("Please provide a covariance kernel!")              # R/spsample_beta.R:27
+    code = _code(cov_type)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n = y.shape[0]
+    X = np.asarray(X, dtype=np.float64).reshape(n, -1)
+    p = X.shape[1]
+    coords = f64(coords, "F")
+    phi = f64(np.asarray(phi).reshape(-1), "C")
+    sig2 = f64(np.asarray(sig2).reshape(-1), "C")
+    tau2 = f64(np.asarray(tau2).reshape(-1), "C")
+    S = phi.shape[0]
+    if eps_beta is None or eps_z is None:
+        rng = np.random.default_rng() if rng is None else rng
+        eps_beta = rng.standard_normal((S, p)) if eps_beta is None else eps_beta
+        eps_z = rng.standard_normal((S, n)) if eps_z is None else eps_z
+    eps_beta = np.asarray(eps_beta, dtype=np.float64).reshape(S, p)
+    eps_z = f64(np.asarray(eps_z).reshape(S, n), "C")
+    XtX = X.T @ X                                                             # :30
+    Xty = X.T @ (y - y.mean())
+    beta = np.empty((S, p))
+    for s in range(S):                                                        # p x p block, :76-78
+        post_sd = np.linalg.inv(1e-4 * np.eye(p) + XtX / tau2[s])
+        post_sd = (post_sd + post_sd.T) / 2
+        post_mean = post_sd @ Xty / tau2[s]
+        beta[s] = np.linalg.cholesky(post_sd) @ eps_beta[s] + post_mean        # crossprod(chol(.), eps) = L eps
+    w = f64((y[None, :] - beta @ X.T) / tau2[:, None], "C")                   # (y - X beta)/tau2, :92
+    z = np.empty((n, S), dtype=np.float64)                                    # S x n column-major
+    bad = np.zeros(S, dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    rc = load().spw_spsample_run(code, n, ptr(coords), S, ptr(phi), ptr(sig2), ptr(tau2), ptr(w), ptr(eps_z),
+                                 ptr(z), ptr(bad), ptr(info))
+    check(rc, info)
+    z = np.ascontiguousarray(z.T)
+    beta0 = np.empty(S)
+    z_last = None
+    for s in range(S):                                                        # "Bad Iteration" rule, :85-89 (one chunk)
+        if bad[s]:
+            if not silent:
+                print("Bad Iteration::", s + 1)
+            z[s] = 0.0 if s == 0 else (z[s - 1] if s == 1 else np.median(z[:s], axis=0))
+            beta0[s] = z_last.mean() if z_last is not None else np.nan        # :99 reads the last drawn z
+        else:
+            z_last = z[s]
+            beta0[s] = z[s].mean()
+    return {"z": z, "beta0": beta0, "beta": beta}
+
+
 def hpd_summary(draws, nbatch, prob=0.95):
     """Batch medians + median + HPD for one component: draws [S x G] -> [G x 3] (R/spatial_gradient.R:391-419)."""
     d = f64(draws, "F")

@@ -300,6 +300,66 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   return SPW_OK;
 }
 
+// ---- spsample: Gibbs recovery of z for a batch of (phi, sig2, tau2) draws (device pointers) -----------------
+// R/spsample_beta.R:50-100 without the p x p regression block (done by the host):
+//   R.inv.Z = chol2inv(chol(R.Z))            -> Linv^T Linv from the triangular inverse        (:70)
+//   Sig.Z.in = R.inv.Z/sig2 + I/tau2         -> scale_add_diag                                 (:83)
+//   Sig.Z = chol2inv(chol(Sig.Z.in))         -> second factorisation + inverse + Gram          (:84,91)
+//   mu.Z = crossprod(Sig.Z, w)               -> gemv (w = (y - X beta)/tau2 from the host)     (:92)
+//   z = crossprod(chol(Sig.Z), eps) + mu.Z   -> third factorisation, lower-triangular matvec   (:93)
+// jitter[b] is added to the diagonal of R.Z (0, or 1e-4 on the retry of :71).
+// status_k[b] != 0: chol(R.Z) failed; status_bad[b] != 0: chol(Sig.Z.in) failed ("Bad Iteration", :85).
+static int spsample_shard(int type, int n, const double* cx, const double* cy, int S, const double* phi,
+                          const double* inv_sig2, const double* inv_tau2, const double* jitter, const double* w,
+                          const double* eps, long long ldv, double* z_out, int* h_status_k, int* h_status_bad,
+                          cudaStream_t st) {
+  if (S == 0) return SPW_OK;
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  const long long ld = pad_ld(n);
+  const int nblk = ceil_div(n, NB);
+  const size_t per_sample = 2 * (size_t)n * ld * sizeof(double) + (size_t)ld * sizeof(double) +
+                            (size_t)nblk * NB * NB * sizeof(double) + 64;
+  const size_t budget = workspace_budget();
+  int B = (int)std::min<size_t>((size_t)std::min(S, 512), budget / per_sample);
+  if (B < 1) { set_error("spw_spsample: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 0, B < 4 ? 1 : 0, &plan));
+  void* wsp;
+  SPW_TRY(get_workspace(*ctx, per_sample * B + 4096, &wsp));
+  Carver cv(wsp);
+  double* Lb = cv.take<double>((size_t)B * n * ld);
+  double* Li = cv.take<double>((size_t)B * n * ld);
+  double* mu = cv.take<double>((size_t)B * ld);
+  double* dinv = cv.take<double>((size_t)B * nblk * NB * NB);
+  int* status = cv.take<int>((size_t)3 * B);
+  MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld};
+  std::vector<int> hs(3 * (size_t)B);
+  for (int s0 = 0; s0 < S; s0 += B) {
+    const int nb = std::min(B, S - s0);
+    SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 3 * B, st));
+    SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, jitter + s0, 1, L, nb, 1, st));
+    SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status, st));
+    SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    SPW_TRY(gram_of_inverse_batched(*plan, Linv, L, nb, st));                       // R.inv.Z
+    SPW_TRY(scale_add_diag_batched(n, L, inv_sig2 + s0, inv_tau2 + s0, nb, st));    // Sig.Z.in
+    SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status + B, st));
+    SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    SPW_TRY(gram_of_inverse_batched(*plan, Linv, L, nb, st));                       // Sig.Z
+    SPW_TRY(gemv_batched(n, L, w + (long long)s0 * ldv, ldv, nullptr, 0, mu, ld, 0, nb, st));   // mu.Z
+    SPW_TRY(potrf_batched(*plan, L, dinv, nullptr, nb, status + 2 * B, st));        // chol(Sig.Z)
+    // z = t(chol(Sig.Z)) eps + mu.Z: the upper factor's transpose is this library's lower factor
+    SPW_TRY(gemv_batched(n, L, eps + (long long)s0 * ldv, ldv, mu, ld, z_out + (long long)s0 * ldv, ldv, 1, nb, st));
+    SPW_CUDA(cudaMemcpyAsync(hs.data(), status, sizeof(int) * 3 * B, cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < nb; ++b) {
+      h_status_k[s0 + b] = hs[b];
+      h_status_bad[s0 + b] = hs[b] ? 0 : (hs[B + b] ? hs[B + b] : hs[2 * B + b]);
+    }
+  }
+  return SPW_OK;
+}
+
 // small RAII helper for temporary device buffers of the host-pointer entry points
 struct DevBuf {
   void* p = nullptr;
@@ -747,6 +807,72 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
   return SPW_OK;
 }
 
+int spw_spsample_run(int type, int n, const double* coords, int S, const double* phi, const double* sig2,
+                     const double* tau2, const double* w, const double* eps, double* out_z, int* bad, int* info) {
+  if (type < 0 || type > 2 || n < 1 || S < 0 || !coords || (S && (!phi || !sig2 || !tau2 || !w || !eps || !out_z))) {
+    set_error("spw_spsample_run: bad arguments");
+    return SPW_ERR_ARG;
+  }
+  if (info) info[0] = info[1] = info[2] = info[3] = 0;
+  if (S == 0) return SPW_OK;
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const long long ldv = pad_ld(n);
+  std::vector<double> h_par(4 * (size_t)S);
+  for (int s = 0; s < S; ++s) {
+    h_par[s] = phi[s];
+    h_par[S + s] = 1.0 / sig2[s];
+    h_par[2 * (size_t)S + s] = 1.0 / tau2[s];
+    h_par[3 * (size_t)S + s] = 0.0;
+  }
+  DevBuf dc, dpar, dwr, dw, der, de, dz, dzr;
+  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
+  SPW_TRY(dpar.alloc(sizeof(double) * 4 * S));
+  SPW_TRY(dwr.alloc(sizeof(double) * (size_t)S * n));
+  SPW_TRY(dw.alloc(sizeof(double) * (size_t)S * ldv));
+  SPW_TRY(der.alloc(sizeof(double) * (size_t)S * n));
+  SPW_TRY(de.alloc(sizeof(double) * (size_t)S * ldv));
+  SPW_TRY(dz.alloc(sizeof(double) * (size_t)S * ldv));
+  SPW_TRY(dzr.alloc(sizeof(double) * (size_t)S * n));
+  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dpar.p, h_par.data(), sizeof(double) * 4 * S, cudaMemcpyHostToDevice, st));
+  // w and eps are n x S column-major == [S][n] row-major: repack to the padded leading dimension
+  SPW_CUDA(cudaMemcpyAsync(dwr.p, w, sizeof(double) * (size_t)S * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(der.p, eps, sizeof(double) * (size_t)S * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpy2DAsync(dw.p, sizeof(double) * ldv, dwr.p, sizeof(double) * n, sizeof(double) * n, S,
+                             cudaMemcpyDeviceToDevice, st));
+  SPW_CUDA(cudaMemcpy2DAsync(de.p, sizeof(double) * ldv, der.p, sizeof(double) * n, sizeof(double) * n, S,
+                             cudaMemcpyDeviceToDevice, st));
+  std::vector<int> sk(S), sb(S);
+  double* par = dpar.as<double>();
+  SPW_TRY(spsample_shard(type, n, dc.as<double>(), dc.as<double>() + n, S, par, par + S, par + 2 * (size_t)S,
+                         par + 3 * (size_t)S, dw.as<double>(), de.as<double>(), ldv, dz.as<double>(), sk.data(),
+                         sb.data(), st));
+  // R/spsample_beta.R:70-71: samples whose chol(R.Z) failed are redone once with R.Z + 1e-4 I
+  for (int s = 0; s < S; ++s) {
+    if (!sk[s]) continue;
+    const double jit = 1e-4;
+    SPW_CUDA(cudaMemcpyAsync(par + 3 * (size_t)S + s, &jit, sizeof(double), cudaMemcpyHostToDevice, st));
+    int k1 = 0, b1 = 0;
+    SPW_TRY(spsample_shard(type, n, dc.as<double>(), dc.as<double>() + n, 1, par + s, par + S + s, par + 2 * (size_t)S + s,
+                           par + 3 * (size_t)S + s, dw.as<double>() + (size_t)s * ldv, de.as<double>() + (size_t)s * ldv, ldv,
+                           dz.as<double>() + (size_t)s * ldv, &k1, &b1, st));
+    if (k1) {   // the reference would stop here: chol() of the jittered matrix failed too
+      if (info) { info[0] = s + 1; info[1] = k1; info[2] = 1; }
+      set_error("spsample: sample %d: chol(R.Z + 1e-4 I) failed (leading minor %d)", s + 1, k1);
+      return SPW_ERR_NOT_PD;
+    }
+    sb[s] = b1;
+  }
+  for (int s = 0; s < S; ++s) bad[s] = sb[s];
+  // [S][ldv] -> S x n column-major (out_z[s + S*k])
+  SPW_TRY(transpose_batched(S, n, dz.as<double>(), ldv, 0, dzr.as<double>(), S, 0, 1, st));
+  SPW_CUDA(cudaMemcpyAsync(out_z, dzr.p, sizeof(double) * (size_t)S * n, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
 int spw_hpd_summary_dev(int S, int g, int ncomp, int nbatch, double prob, const double* draws_dev, double* out_dev,
                         void* stream) {
   DeviceCtx* ctx;
@@ -787,6 +913,27 @@ int spw_hpd_summary(int S, int g, int nbatch, double prob, const double* draws, 
 int spw_cov_p(const int* type, const int* n, const double* coords, const double* phi, const double* sig2, double* out,
               int* status) {
   const int rc = spw_cov(*type, *n, coords, *phi, *sig2, out);
+  if (status) *status = rc;
+  return rc;
+}
+
+int spw_hlm_run_p(const int* n, const double* coords, const double* y, const int* type, const int* niter,
+                  const int* nburn, const int* report, const double* hyper, const double* norm, const double* unif,
+                  const int* want_trgt, double* out_sig2, double* out_tau2, double* out_phi, double* out_trgt,
+                  double* out_accept, double* out_tuning, int* info, int* status) {
+  const int rc = spw_hlm_run(*n, coords, y, *type, *niter, *nburn, *report, hyper[0], hyper[1], hyper[2], hyper[3],
+                             hyper[4], hyper[5], norm, unif, *want_trgt, out_sig2, out_tau2, out_phi, out_trgt,
+                             out_accept, out_tuning, info);
+  if (status) *status = rc;
+  return rc;
+}
+
+int spw_gradient_run_p(const int* type, const int* n, const double* coords, const int* g, const double* grid,
+                       const int* S, const double* phi, const double* sig2, const double* z, const double* eps,
+                       const int* ngpu, const int* nbatch, const double* prob, const int* want_draws, double* out_draws,
+                       double* out_summary, int* info, int* status) {
+  const int rc = spw_gradient_run(*type, *n, coords, *g, grid, *S, phi, sig2, z, eps, *ngpu, *nbatch, *prob,
+                                  *want_draws ? out_draws : nullptr, out_summary, nullptr, nullptr, info);
   if (status) *status = rc;
   return rc;
 }

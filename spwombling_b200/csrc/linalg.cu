@@ -87,6 +87,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int k0 = kt * G_BK;
     bool masked = false;
     if (t.a_tri == 1) masked |= (k0 + G_BK - 1 > t.a_lim0);
+    if (t.a_tri == 2) masked |= (k0 < t.a_lim0 + Cfg::BM - 1);
     if (t.b_tri == 1) masked |= (k0 + G_BK - 1 > t.b_lim0);
     if (t.b_tri == 2) masked |= (k0 < t.b_lim0 + Cfg::BN - 1);
 #pragma unroll
@@ -102,6 +103,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < Cfg::MF; ++i)
             if (k > t.a_lim0 + warp_m * Cfg::WM + i * 8 + g) a[i] = 0.0;
+        } else if (t.a_tri == 2) {
+#pragma unroll
+          for (int i = 0; i < Cfg::MF; ++i)
+            if (k < t.a_lim0 + warp_m * Cfg::WM + i * 8 + g) a[i] = 0.0;
         }
         if (t.b_tri == 1) {
 #pragma unroll
@@ -559,6 +564,23 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
     plan.inv1.push_back(r1);
     plan.inv2.push_back(r2);
   }
+  // P = T^T T for a lower-triangular T whose transpose sits in the upper triangle of the same buffer (the state the
+  // triangular inverse leaves): P[m][n] = sum_{k >= max(m, n)} TT[m][k] TT[n][k]; lower tiles, mirrored on store
+  plan.prod.begin = (int)tasks.size();
+  for (int m0 = 0; m0 < n; m0 += T)
+    for (int n0 = 0; n0 <= m0; n0 += T) {
+      GemmTask t = blank_task();
+      t.a_row = m0; t.a_col = m0;
+      t.b_row = n0; t.b_col = m0;
+      t.c_row = m0; t.c_col = n0;
+      t.ct_row = n0; t.ct_col = m0;
+      t.m = std::min(T, n - m0); t.n = std::min(T, n - n0); t.k = n - m0;
+      t.a_tri = 2; t.a_lim0 = 0;
+      t.b_tri = (n0 == m0) ? 2 : 0; t.b_lim0 = 0;
+      t.flags = GT_STORE | GT_STORE_T;
+      tasks.push_back(t);
+    }
+  plan.prod.count = (int)tasks.size() - plan.prod.begin;
   plan.n_tasks = (int)tasks.size();
   if (plan.n_tasks > 0) {
     SPW_CUDA(cudaMalloc(&plan.d_tasks, sizeof(GemmTask) * tasks.size()));
@@ -653,6 +675,63 @@ int trtri_batched(const LinalgPlan& plan, MatView L, MatView linv, int batch, cu
     SPW_TRY(launch_gemm_tasks(0, plan.d_tasks + plan.inv1[lev].begin, plan.inv1[lev].count, batch, opL, opI, none, L, 1.0, st));
     SPW_TRY(launch_gemm_tasks(0, plan.d_tasks + plan.inv2[lev].begin, plan.inv2[lev].count, batch, opI, opL, linv, linv, -1.0, st));
   }
+  return SPW_OK;
+}
+
+int gram_of_inverse_batched(const LinalgPlan& plan, MatView linv, MatView out, int batch, cudaStream_t st) {
+  Operand opI{linv, plan.n, plan.n};
+  return launch_gemm_tasks(0, plan.d_tasks + plan.prod.begin, plan.prod.count, batch, opI, opI, out, out, 1.0, st);
+}
+
+// out_b = alpha_b * out_b + diag_b * I   (full n x n matrices)
+__global__ void __launch_bounds__(256)
+scale_add_diag_kernel(int n, MatView M, const double* __restrict__ alpha, const double* __restrict__ diag) {
+  const int b = blockIdx.z;
+  const int r = blockIdx.y;
+  const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= n) return;
+  double* p = M.p + (long long)b * M.stride + (long long)r * M.ld + c;
+  const double a = alpha[b], d = diag[b];
+  if (c + 1 < n) {
+    double2 v = *reinterpret_cast<double2*>(p);
+    v.x = a * v.x + ((r == c) ? d : 0.0);
+    v.y = a * v.y + ((r == c + 1) ? d : 0.0);
+    *reinterpret_cast<double2*>(p) = v;
+  } else {
+    p[0] = a * p[0] + ((r == c) ? d : 0.0);
+  }
+}
+
+int scale_add_diag_batched(int n, MatView M, const double* alpha, const double* diag, int batch, cudaStream_t st) {
+  if (batch <= 0) return SPW_OK;
+  if (n > 65535 || batch > 65535) { set_error("scale_add_diag: size limits"); return SPW_ERR_ARG; }
+  scale_add_diag_kernel<<<dim3(ceil_div(ceil_div(n, 2), 256), n, batch), 256, 0, st>>>(n, M, alpha, diag);
+  SPW_LAUNCHED();
+  return SPW_OK;
+}
+
+// v = M x (+ add) for full row-major matrices: one warp per row
+__global__ void __launch_bounds__(256)
+gemv_kernel(int n, MatView M, const double* __restrict__ x, long long ldx, const double* __restrict__ add, long long ldadd,
+            double* __restrict__ v, long long ldv, int lower_only) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* Mp = M.p + (long long)b * M.stride + (long long)row * M.ld;
+  const double* xp = x + (long long)b * ldx;
+  const int kend = lower_only ? row + 1 : n;
+  double s = 0.0;
+  for (int k = lane; k < kend; k += 32) s = fma(Mp[k], xp[k], s);
+  s = warp_sum(s);
+  if (lane == 0) v[(long long)b * ldv + row] = s + (add ? add[(long long)b * ldadd + row] : 0.0);
+}
+
+int gemv_batched(int n, MatView M, const double* x, long long ldx, const double* add, long long ldadd, double* v,
+                 long long ldv, int lower_only, int batch, cudaStream_t st) {
+  if (batch <= 0) return SPW_OK;
+  gemv_kernel<<<dim3(ceil_div(n, 8), batch), 256, 0, st>>>(n, M, x, ldx, add, ldadd, v, ldv, lower_only);
+  SPW_LAUNCHED();
   return SPW_OK;
 }
 

@@ -38,6 +38,7 @@ struct LinalgPlan {
   std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
   std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
   std::vector<ChunkRange> inv1, inv2;           // per trtri level
+  ChunkRange prod{0, 0};                        // T^T T of an inverted factor (spsample)
   GemmTask* d_tasks = nullptr;
   int n_tasks = 0;
 };
@@ -60,6 +61,14 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
 // upper triangle its transpose.  Uses the strict upper triangle of L as scratch.  Requires the
 // level-0 state written by potrf_batched.
 int trtri_batched(const LinalgPlan& plan, MatView L, MatView linv, int batch, cudaStream_t st);
+
+// out = Linv^T Linv (full symmetric matrix) from the state trtri_batched leaves in linv: chol2inv() without dpotri
+int gram_of_inverse_batched(const LinalgPlan& plan, MatView linv, MatView out, int batch, cudaStream_t st);
+// M_b = alpha[b] * M_b + diag[b] * I
+int scale_add_diag_batched(int n, MatView M, const double* alpha, const double* diag, int batch, cudaStream_t st);
+// v_b = M_b x_b (+ add_b); lower_only: use only k <= row
+int gemv_batched(int n, MatView M, const double* x, long long ldx, const double* add, long long ldadd, double* v,
+                 long long ldv, int lower_only, int batch, cudaStream_t st);
 
 // v[b][i] = sum_{k<=i} T[b][i][k] * x[b][k]   (lower-triangular matrix-vector product)
 int trmv_lower_batched(int n, MatView T, const double* x, long long ldx, double* v, long long ldv, int batch,
