@@ -440,11 +440,6 @@ int spw_debug_diag_timing(long long* out5) {
     SPW_CUDA(cudaMemset(g_diag_dbg, 0, 8 * sizeof(long long)));
     return SPW_OK;
   }
-  if (out5[0] < 0) {   // set the experiment mode (timing studies only)
-    const long long mode = -out5[0];
-    SPW_CUDA(cudaMemcpy(g_diag_dbg + 7, &mode, sizeof(long long), cudaMemcpyHostToDevice));
-    return SPW_OK;
-  }
   SPW_CUDA(cudaDeviceSynchronize());
   SPW_CUDA(cudaMemcpy(out5, g_diag_dbg, 5 * sizeof(long long), cudaMemcpyDeviceToHost));
   return SPW_OK;

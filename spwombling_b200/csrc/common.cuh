@@ -63,17 +63,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// 1/sqrt(x) to full double precision on a short dependency chain: hardware approximation (2^-22) + two Newton
-// steps (the library rsqrt() costs ~250 cycles of latency, this ~100); non-positive / non-finite x give NaN or the
-// IEEE limits through the same formula, which the callers' pivot checks catch.
+// 1/sqrt(x) to full double precision on a short dependency chain: hardware approximation (relative error 2^-22)
+// followed by ONE cubically convergent (Halley) step, y (1 + e/2 + 3 e^2/8) with e = 1 - x y^2 -- four dependent
+// FP64 operations (the library rsqrt() costs ~10).  Non-positive / non-finite x propagate NaN or the IEEE limits
+// through the same formula, which the callers' pivot checks catch.
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
-  double e = fma(-(x * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  e = fma(-(x * y), y, 1.0);
-  y = fma(0.5 * y, e, y);
-  return y;
+  const double e = fma(-(x * y), y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
 }
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }

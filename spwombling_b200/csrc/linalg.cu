@@ -176,48 +176,55 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 constexpr int DIAG_THREADS = 256;
 long long* g_diag_dbg = nullptr;   // optional device buffer of 8 cycle counters (spw_debug_diag_timing)
 
-template <int S16>
+template <int S>
 __device__ __forceinline__ void diag_inverse_level(double (*Ls)[NB + 1], double (*Xs)[NB + 1], double (*Ts)[33], int tid) {
-  // pairs (b1 = 2 S16 p, b2 = b1 + S16); each thread owns a 1 x 2 (S16 = 16) or 2 x 2 (S16 = 32) block of outputs
-  constexpr int MR = (S16 == 16) ? 1 : 2;
-  constexpr int TPP = (S16 / MR) * (S16 / 2);          // threads per pair: 128 (two pairs) or 256 (one pair)
+  // pairs (b1 = 2 S p, b2 = b1 + S), p < NB / (2 S); each thread owns a 1 x 2 (S <= 16) or 2 x 2 (S = 32) block of
+  // the S x S outputs of its pair; threads beyond the work only take part in the barriers
+  constexpr int MR = (S == 32) ? 2 : 1;
+  constexpr int TPP = (S / MR) * (S / 2);                 // threads per pair
+  constexpr int NEED = TPP * (NB / (2 * S));              // 64, 128, 256, 256 for S = 4, 8, 16, 32
+  const bool work = tid < NEED;
   const int p = tid / TPP, e = tid % TPP;
-  const int m0 = (e / (S16 / 2)) * MR, n0 = (e % (S16 / 2)) * 2;
-  const int b1 = 2 * S16 * p, b2 = b1 + S16;
+  const int m0 = (e / (S / 2)) * MR, n0 = (e % (S / 2)) * 2;
+  const int b1 = 2 * S * p, b2 = b1 + S;
   double acc[MR][2];
 #pragma unroll
   for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.0;
+  if (work) {
 #pragma unroll
-  for (int k = 0; k < S16; ++k) {            // T = L21 X11   (X11 is lower triangular: zeros supply the k >= n bound)
-    const double x0 = Xs[b1 + k][b1 + n0], x1 = Xs[b1 + k][b1 + n0 + 1];
+    for (int k = 0; k < S; ++k) {              // T = L21 X11   (X11 lower triangular: zeros supply the k >= n bound)
+      const double x0 = Xs[b1 + k][b1 + n0], x1 = Xs[b1 + k][b1 + n0 + 1];
+#pragma unroll
+      for (int i = 0; i < MR; ++i) {
+        const double l = Ls[b2 + m0 + i][b1 + k];
+        acc[i][0] = fma(l, x0, acc[i][0]);
+        acc[i][1] = fma(l, x1, acc[i][1]);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < MR; ++i) {
-      const double l = Ls[b2 + m0 + i][b1 + k];
-      acc[i][0] = fma(l, x0, acc[i][0]);
-      acc[i][1] = fma(l, x1, acc[i][1]);
+      Ts[p * S + m0 + i][n0] = acc[i][0];
+      Ts[p * S + m0 + i][n0 + 1] = acc[i][1];
+      acc[i][0] = acc[i][1] = 0.0;
     }
-  }
-#pragma unroll
-  for (int i = 0; i < MR; ++i) {
-    Ts[p * S16 + m0 + i][n0] = acc[i][0];
-    Ts[p * S16 + m0 + i][n0 + 1] = acc[i][1];
-    acc[i][0] = acc[i][1] = 0.0;
   }
   __syncthreads();
+  if (work) {
 #pragma unroll
-  for (int k = 0; k < S16; ++k) {            // X21 = -X22 T   (X22 lower triangular: zeros supply the k <= m bound)
-    const double t0 = Ts[p * S16 + k][n0], t1 = Ts[p * S16 + k][n0 + 1];
+    for (int k = 0; k < S; ++k) {              // X21 = -X22 T   (X22 lower triangular: zeros supply the k <= m bound)
+      const double t0 = Ts[p * S + k][n0], t1 = Ts[p * S + k][n0 + 1];
+#pragma unroll
+      for (int i = 0; i < MR; ++i) {
+        const double x = Xs[b2 + m0 + i][b2 + k];
+        acc[i][0] = fma(x, t0, acc[i][0]);
+        acc[i][1] = fma(x, t1, acc[i][1]);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < MR; ++i) {
-      const double x = Xs[b2 + m0 + i][b2 + k];
-      acc[i][0] = fma(x, t0, acc[i][0]);
-      acc[i][1] = fma(x, t1, acc[i][1]);
+      Xs[b2 + m0 + i][b1 + n0] = -acc[i][0];
+      Xs[b2 + m0 + i][b1 + n0 + 1] = -acc[i][1];
     }
-  }
-#pragma unroll
-  for (int i = 0; i < MR; ++i) {
-    Xs[b2 + m0 + i][b1 + n0] = -acc[i][0];
-    Xs[b2 + m0 + i][b1 + n0 + 1] = -acc[i][1];
   }
   __syncthreads();
 }
@@ -227,13 +234,13 @@ diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nbl
                    int* __restrict__ status, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double diag_smem[];
   long long t0 = 0;
-  const int xmode = dbg ? (int)dbg[7] : 0;   // timing experiments only (results are wrong when != 0)
   if (dbg && threadIdx.x == 0 && blockIdx.x == 0) t0 = clock64();
 #define DIAG_MARK(i) if (dbg && threadIdx.x == 0 && blockIdx.x == 0) dbg[i] = clock64() - t0;
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem);
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem + NB * (NB + 1));
-  __shared__ __align__(16) double Tb[2][16][16];      // published raw tiles of the current tile column
-  __shared__ double rdiag[NB];
+  __shared__ __align__(16) double Tb[2][16][16];      // published raw pivot tile (double-buffered by column parity)
+  __shared__ __align__(16) double Xb[16][16];         // solved 4 x 4 blocks of the current tile column
+  __shared__ double Xd[16][16];                       // inverses of the 4 x 4 diagonal tiles
   __shared__ double Ts[32][33];
   __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -254,89 +261,91 @@ diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nbl
       a[ii][kk] = v;
     }
   DIAG_MARK(0)
-  // ---- Cholesky, four pivots per barrier ----
+  // ---- Cholesky, four pivots at a time, two barriers per tile column: (A) the owners of tile column jb factor the
+  //      4 x 4 pivot tile (redundantly, 16 threads) and solve their own 4 x 4 block X = C Ld^-T, which is final;
+  //      (B) every remaining tile takes its rank-4 update from the published X blocks ----
 #pragma unroll 1
   for (int jb = 0; jb < NB / 4; ++jb) {
     double (*T)[16] = Tb[jb & 1];
-    if (tk == jb && active) {
+    if (tk == jb && ti == jb) {              // publish the raw pivot tile
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int kk = 0; kk < 4; kk += 2)
-          *reinterpret_cast<double2*>(&T[ti][ii * 4 + kk]) = make_double2(a[ii][kk], a[ii][kk + 1]);
+          *reinterpret_cast<double2*>(&T[jb][ii * 4 + kk]) = make_double2(a[ii][kk], a[ii][kk + 1]);
     }
     __syncthreads();
-    if (active && tk >= jb) {
+    if (tk == jb && active) {
       const double* D = T[jb];
-      // 4 x 4 Cholesky of the pivot tile (lower part), with reciprocal square roots
-      if (xmode == 3) continue;
-      const double q0 = D[0], rs0 = (xmode == 1) ? q0 * 0.5 : fast_rsqrt(q0);
+      const double q0 = D[0], rs0 = fast_rsqrt(q0);
       const double l10 = D[4] * rs0, l20 = D[8] * rs0, l30 = D[12] * rs0;
-      const double q1 = fma(-l10, l10, D[5]), rs1 = (xmode == 1) ? q1 * 0.5 : fast_rsqrt(q1);
+      const double q1 = fma(-l10, l10, D[5]), rs1 = fast_rsqrt(q1);
       const double l21 = fma(-l20, l10, D[9]) * rs1, l31 = fma(-l30, l10, D[13]) * rs1;
-      const double q2 = fma(-l21, l21, fma(-l20, l20, D[10])), rs2 = (xmode == 1) ? q2 * 0.5 : fast_rsqrt(q2);
+      const double q2 = fma(-l21, l21, fma(-l20, l20, D[10])), rs2 = fast_rsqrt(q2);
       const double l32 = fma(-l31, l21, fma(-l30, l20, D[14])) * rs2;
-      const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[15]))), rs3 = (xmode == 1) ? q3 * 0.5 : fast_rsqrt(q3);
-      if (ti == jb) {                       // the diagonal tile itself: final factor entries (and the pivot check)
-        if (tk == jb) {
-          int first_bad = 0;
-          if (!(q3 > 0.0)) first_bad = 4;
-          if (!(q2 > 0.0)) first_bad = 3;
-          if (!(q1 > 0.0)) first_bad = 2;
-          if (!(q0 > 0.0)) first_bad = 1;
-          if (first_bad && bad == 0) bad = r0 + 4 * jb + first_bad;
-          a[0][0] = q0 * rs0;
-          a[1][0] = l10; a[1][1] = q1 * rs1;
-          a[2][0] = l20; a[2][1] = l21; a[2][2] = q2 * rs2;
-          a[3][0] = l30; a[3][1] = l31; a[3][2] = l32; a[3][3] = q3 * rs3;
-          a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
-        }
-      } else {
-        // Xi = Ci Ld^-T (rows of this thread's row tile), Xk = Ck Ld^-T (rows of its column tile)
-        double xi[4][4], xk[4][4];
-        const double* Ci = T[ti];
+      const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[15]))), rs3 = fast_rsqrt(q3);
+      if (ti == jb) {                        // the diagonal tile: final factor entries and the pivot check
+        int first_bad = 0;
+        if (!(q3 > 0.0)) first_bad = 4;
+        if (!(q2 > 0.0)) first_bad = 3;
+        if (!(q1 > 0.0)) first_bad = 2;
+        if (!(q0 > 0.0)) first_bad = 1;
+        if (first_bad && bad == 0) bad = r0 + 4 * jb + first_bad;
+        a[0][0] = q0 * rs0;
+        a[1][0] = l10; a[1][1] = q1 * rs1;
+        a[2][0] = l20; a[2][1] = l21; a[2][2] = q2 * rs2;
+        a[3][0] = l30; a[3][1] = l31; a[3][2] = l32; a[3][3] = q3 * rs3;
+        a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
+        // 4 x 4 inverse of the diagonal tile: seeds the blocked inverse below
+        const double i00 = rs0, i11 = rs1, i22 = rs2, i33 = rs3;
+        const double i10 = -l10 * i00 * i11;
+        const double i21 = -l21 * i11 * i22;
+        const double i32 = -l32 * i22 * i33;
+        const double i20 = -(l20 * i00 + l21 * i10) * i22;
+        const double i31 = -(l31 * i11 + l32 * i21) * i33;
+        const double i30 = -(l30 * i00 + l31 * i10 + l32 * i20) * i33;
+        double* xd = &Xd[jb][0];
+        xd[0] = i00; xd[1] = 0.0; xd[2] = 0.0; xd[3] = 0.0;
+        xd[4] = i10; xd[5] = i11; xd[6] = 0.0; xd[7] = 0.0;
+        xd[8] = i20; xd[9] = i21; xd[10] = i22; xd[11] = 0.0;
+        xd[12] = i30; xd[13] = i31; xd[14] = i32; xd[15] = i33;
+      } else {                               // below the diagonal: X = C Ld^-T, final, and published for the updates
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const double c0 = Ci[4 * r], c1 = Ci[4 * r + 1], c2 = Ci[4 * r + 2], c3 = Ci[4 * r + 3];
-          xi[r][0] = c0 * rs0;
-          xi[r][1] = fma(-xi[r][0], l10, c1) * rs1;
-          xi[r][2] = fma(-xi[r][1], l21, fma(-xi[r][0], l20, c2)) * rs2;
-          xi[r][3] = fma(-xi[r][2], l32, fma(-xi[r][1], l31, fma(-xi[r][0], l30, c3))) * rs3;
-        }
-        if (tk == jb) {                     // column owner below the diagonal: these are its final factor entries
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) a[r][c] = xi[r][c];
-        } else {
-          if (tk == ti || xmode == 2) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) xk[r][c] = xi[r][c];
-          } else {
-            const double* Ck = T[tk];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const double c0 = Ck[4 * r], c1 = Ck[4 * r + 1], c2 = Ck[4 * r + 2], c3 = Ck[4 * r + 3];
-              xk[r][0] = c0 * rs0;
-              xk[r][1] = fma(-xk[r][0], l10, c1) * rs1;
-              xk[r][2] = fma(-xk[r][1], l21, fma(-xk[r][0], l20, c2)) * rs2;
-              xk[r][3] = fma(-xk[r][2], l32, fma(-xk[r][1], l31, fma(-xk[r][0], l30, c3))) * rs3;
-            }
-          }
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              double s = a[ii][kk];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) s = fma(-xi[ii][c], xk[kk][c], s);
-              a[ii][kk] = s;
-            }
+          const double c0 = a[r][0], c1 = a[r][1], c2 = a[r][2], c3 = a[r][3];
+          const double x0 = c0 * rs0;
+          const double x1 = fma(-x0, l10, c1) * rs1;
+          const double x2 = fma(-x1, l21, fma(-x0, l20, c2)) * rs2;
+          const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, c3))) * rs3;
+          a[r][0] = x0; a[r][1] = x1; a[r][2] = x2; a[r][3] = x3;
+          *reinterpret_cast<double2*>(&Xb[ti][4 * r]) = make_double2(x0, x1);
+          *reinterpret_cast<double2*>(&Xb[ti][4 * r + 2]) = make_double2(x2, x3);
         }
       }
     }
+    __syncthreads();
+    if (active && tk > jb) {
+      double xi[4][4], xk[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double2 u0 = *reinterpret_cast<const double2*>(&Xb[ti][4 * r]);
+        const double2 u1 = *reinterpret_cast<const double2*>(&Xb[ti][4 * r + 2]);
+        xi[r][0] = u0.x; xi[r][1] = u0.y; xi[r][2] = u1.x; xi[r][3] = u1.y;
+        const double2 w0 = *reinterpret_cast<const double2*>(&Xb[tk][4 * r]);
+        const double2 w1 = *reinterpret_cast<const double2*>(&Xb[tk][4 * r + 2]);
+        xk[r][0] = w0.x; xk[r][1] = w0.y; xk[r][2] = w1.x; xk[r][3] = w1.y;
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          double sacc = a[ii][kk];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sacc = fma(-xi[ii][c], xk[kk][c], sacc);
+          a[ii][kk] = sacc;
+        }
+    }
+    // Xb is rewritten only after the next column's barrier (A), which every reader of this column has passed
   }
   DIAG_MARK(1)
   // ---- factor -> shared memory (zeros above the diagonal) and back to global ----
@@ -353,22 +362,14 @@ diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nbl
   __syncthreads();
   if (tid == 0 && bad) atomicCAS(&status[b], 0, bad);
   DIAG_MARK(2)
-  // ---- inverse X = L^-1 ----
-  if (tid < NB) rdiag[tid] = 1.0 / Ls[tid][tid];
-  __syncthreads();
-  if (tid < NB) {                           // 16 x 16 diagonal blocks: one thread per column, forward substitution
-    const int d0 = (tid >> 4) * 16, c = tid & 15;
-    double x[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      double s0 = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int k = 0; k < r; ++k) s0 = fma(-Ls[d0 + r][d0 + k], (k >= c) ? x[k] : 0.0, s0);
-      x[r] = (r >= c) ? s0 * rdiag[d0 + r] : 0.0;
-      Xs[d0 + r][d0 + c] = x[r];
-    }
+  // ---- inverse X = L^-1: 4 x 4 diagonal tiles (computed with the factor), then X21 = -X22 (L21 X11) level by level ----
+  if (tid < NB * 4) {
+    const int t4 = tid >> 4, e = tid & 15;
+    Xs[4 * t4 + (e >> 2)][4 * t4 + (e & 3)] = Xd[t4][e];
   }
   __syncthreads();
+  diag_inverse_level<4>(Ls, Xs, Ts, tid);
+  diag_inverse_level<8>(Ls, Xs, Ts, tid);
   diag_inverse_level<16>(Ls, Xs, Ts, tid);
   diag_inverse_level<32>(Ls, Xs, Ts, tid);
   DIAG_MARK(3)
