@@ -145,6 +145,15 @@ int spw_hpd_summary_dev(int S, int g, int ncomp, int nbatch, double prob, const 
 /* [S][ncomp][g] (device) -> R layout [ncomp][g][S] (device): the S x g column-major matrices */
 int spw_draws_to_r_layout_dev(int S, int g, int ncomp, const double* draws_dev, double* out_dev, void* stream);
 
+/* Posterior surface analysis (README.md:123-177): from the five S x g draw matrices
+ * (draws [S x g x 5] column-major, components s1, s2, s11, s12, s22) compute per (sample, grid point) the Hessian
+ * determinant, its two eigenvalues (decreasing), the Laplacian and the divergence (out_derived [S x g x 5], optional)
+ * and their batch-median / HPD summaries (out_summary [g x 3 x 5] column-major, optional). */
+int spw_surface_analysis(int S, int g, const double* draws, int nbatch, double prob, double* out_summary,
+                         double* out_derived);
+/* device variant on the internal layout: draws_dev / out_dev [S][5][g] */
+int spw_surface_analysis_dev(int S, int g, const double* draws_dev, double* out_dev, void* stream);
+
 /* .C()-compatible variants (every argument a pointer, no R headers needed) ------------------------ */
 int spw_cov_p(const int* type, const int* n, const double* coords, const double* phi, const double* sig2,
               double* out, int* status);

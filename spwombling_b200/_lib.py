@@ -44,6 +44,8 @@ SIGNATURES = {
     "spw_hpd_summary": (c_int, [c_int, c_int, c_int, c_dbl, c_vp, c_vp]),
     "spw_hpd_summary_dev": (c_int, [c_int, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
     "spw_draws_to_r_layout_dev": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "spw_surface_analysis": (c_int, [c_int, c_int, c_vp, c_int, c_dbl, c_vp, c_vp]),
+    "spw_surface_analysis_dev": (c_int, [c_int, c_int, c_vp, c_vp, c_vp]),
     "spw_cov_p": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spw_hpd_summary_p": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spw_hlm_run_p": (c_int, [c_vp] * 19),

@@ -274,6 +274,83 @@ def spsample(y=None, X=None, coords=None, phi=None, sig2=None, tau2=None, cov_ty
     return {"z": z, "beta0": beta0, "beta": beta}
 
 
+def bayes_cwomb(coords=None, model=None, cov_type=None, nbatch=None, curve=None, type="riemann.sum", approx=None,
+                verbose=True, rule_len=10, eps=None, rng=None, ngpu=1, rounded=True):
+    """Curvilinear wombling measures along a polyline -- R/spatial_wombling.R:28-36, ``type = "riemann.sum"`` branches
+    (:114-157 matern1, :245-306 matern2, :394-455 gaussian): ``spatial_gradient`` at the curve vertices (GPU path),
+    projection on each segment's unit normal, batch medians + HPD per segment, length-weighted measures.
+    Returns the reference's list as a dict: ``tval, uval, womb1.mcmc, [womb2.mcmc], womb.grad.inf, [womb.curv.inf],
+    womb.measure.inf``.  ``type = "rectilinear"`` is not provided: that branch is broken upstream (``model$phis``,
+    ``1:ntimes`` on a vector -- SURVEY section 8f rank 3)."""
+    if type != "riemann.sum":
+        raise NotImplementedError("bayes_cwomb(type='rectilinear') is broken upstream and not ported (SURVEY 8f rank 3)")
+    curve = np.asarray(curve, dtype=np.float64)
+    d = curve[1:] - curve[:-1]
+    tval = np.sqrt((d ** 2).sum(axis=1))                                   # R/spatial_wombling.R:42
+    uval = d / tval[:, None]                                               # :43
+    u_perp = np.column_stack([uval[:, 1], -uval[:, 0]])                    # :115-119
+    g = spatial_gradient(coords=coords, model=model, cov_type=cov_type, grid_points=curve, nbatch=nbatch,
+                         return_mcmc=True, eps=eps, rng=rng, ngpu=ngpu)
+    s1, s2 = g["grad.s1.mcmc"][:, :-1], g["grad.s2.mcmc"][:, :-1]
+    estval = s1 * u_perp[:, 0] + s2 * u_perp[:, 1]                         # :131-133
+    S = estval.shape[0]
+
+    def seg_inf(mat, strict_pair):
+        inf = hpd_summary(mat, nbatch)                                     # :134-141 (batch medians, median, HPD)
+        if rounded:
+            inf = np.round(inf, 3)
+        if strict_pair:
+            sig = np.where((inf[:, 1] > 0) & (inf[:, 2] > 0), 1.0, np.where((inf[:, 1] < 0) & (inf[:, 2] < 0), -1.0, 0.0))
+        else:
+            sig = np.where(inf[:, 1] > 0, 1.0, np.where(inf[:, 2] < 0, -1.0, 0.0))    # :142-146 (matern1 branch)
+        return np.column_stack([inf, sig])
+
+    def measure(inf, mat):                                                 # :148
+        per_sample = (mat * tval).sum(axis=1) / tval.sum()
+        h = hpd_summary(per_sample[:, None], S)[0]                         # HPD over the S per-sample measures
+        return np.array([(inf[:, 0] * tval).sum() / tval.sum(), h[0], h[1], h[2]])
+
+    out = {"tval": tval, "uval": uval, "womb1.mcmc": estval}
+    grad_inf = seg_inf(estval, cov_type != "matern1")
+    rows = [measure(grad_inf, estval)]
+    if cov_type != "matern1":
+        s11, s12, s22 = (g["grad.%s.mcmc" % k][:, :-1] for k in ("s11", "s12", "s22"))
+        estval1 = s11 * u_perp[:, 0] ** 2 + s22 * u_perp[:, 1] ** 2 + 2 * s12 * u_perp[:, 0] * u_perp[:, 1]   # :266
+        out["womb2.mcmc"] = estval1
+        out["womb.grad.inf"] = grad_inf
+        curv_inf = seg_inf(estval1, True)
+        out["womb.curv.inf"] = curv_inf
+        rows.append(measure(curv_inf, estval1))
+    else:
+        out["womb.grad.inf"] = grad_inf
+    out["womb.measure.inf"] = np.stack(rows)
+    return out
+
+
+SURFACE_NAMES = ("det", "eigen1", "eigen2", "laplace", "div")
+
+
+def surface_analysis(gradient_est, nbatch=100, prob=0.95, return_mcmc=False):
+    """Posterior surface analysis of the README workflow (README.md:123-177): Hessian determinant, eigenvalues,
+    Laplacian and divergence per (sample, grid point) from the ``grad.s*.mcmc`` matrices of ``spatial_gradient``, each
+    summarised by batch medians + HPD with the significance flag of README.md:143-147.
+    Returns ``{name: G x 4 array (estimate, lower, upper, sig)}`` (+ ``name + ".mcmc"``: S x G when ``return_mcmc``)."""
+    mats = [np.asarray(gradient_est["grad.%s.mcmc" % k], dtype=np.float64) for k in COMP_NAMES[5]]
+    S, g = mats[0].shape
+    draws = np.ascontiguousarray(np.stack([m.T for m in mats]))          # [5][g][S] == S x g x 5 column-major
+    summ = np.empty((5, 3, g), dtype=np.float64)
+    derived = np.empty((5, g, S), dtype=np.float64) if return_mcmc else None
+    check(load().spw_surface_analysis(S, g, ptr(draws), int(nbatch), float(prob), ptr(summ), ptr(derived)))
+    out = {}
+    for k, name in enumerate(SURFACE_NAMES):
+        est = summ[k].T
+        sig = np.where((est[:, 1] > 0) & (est[:, 2] > 0), 1.0, np.where((est[:, 1] < 0) & (est[:, 2] < 0), -1.0, 0.0))
+        out[name] = np.column_stack([est, sig])
+        if return_mcmc:
+            out[name + ".mcmc"] = derived[k].T
+    return out
+
+
 def hpd_summary(draws, nbatch, prob=0.95):
     """Batch medians + median + HPD for one component: draws [S x G] -> [G x 3] (R/spatial_gradient.R:391-419)."""
     d = f64(draws, "F")

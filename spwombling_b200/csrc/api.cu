@@ -910,6 +910,43 @@ int spw_hpd_summary(int S, int g, int nbatch, double prob, const double* draws, 
   return SPW_OK;
 }
 
+int spw_surface_analysis_dev(int S, int g, const double* draws_dev, double* out_dev, void* stream) {
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return surface_analysis_dev(S, g, draws_dev, out_dev, st);
+}
+
+int spw_surface_analysis(int S, int g, const double* draws, int nbatch, double prob, double* out_summary,
+                         double* out_derived) {
+  if (S < 1 || g < 1 || !draws || (!out_summary && !out_derived)) { set_error("spw_surface_analysis: bad arguments"); return SPW_ERR_ARG; }
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const size_t cnt = (size_t)S * g * 5;
+  DevBuf din, dt, dd, dsum;
+  SPW_TRY(din.alloc(sizeof(double) * cnt));
+  SPW_TRY(dt.alloc(sizeof(double) * cnt));
+  SPW_TRY(dd.alloc(sizeof(double) * cnt));
+  SPW_CUDA(cudaMemcpyAsync(din.p, draws, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+  // R layout [5][g][S] (S contiguous) -> [S][5][g]
+  SPW_TRY(transpose_batched(5 * g, S, din.as<double>(), S, 0, dt.as<double>(), (long long)5 * g, 0, 1, st));
+  SPW_TRY(surface_analysis_dev(S, g, dt.as<double>(), dd.as<double>(), st));
+  if (out_summary) {
+    SPW_TRY(dsum.alloc(sizeof(double) * 15 * (size_t)g));
+    void* scratch;
+    SPW_TRY(get_scratch(*ctx, hpd_scratch_bytes(S, g, 5, nbatch), &scratch));
+    SPW_TRY(hpd_summary_dev(S, g, 5, nbatch, prob, dd.as<double>(), dsum.as<double>(), scratch, st));
+    SPW_CUDA(cudaMemcpyAsync(out_summary, dsum.p, sizeof(double) * 15 * (size_t)g, cudaMemcpyDeviceToHost, st));
+  }
+  if (out_derived) {
+    SPW_TRY(transpose_batched(S, 5 * g, dd.as<double>(), (long long)5 * g, 0, din.as<double>(), S, 0, 1, st));
+    SPW_CUDA(cudaMemcpyAsync(out_derived, din.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+  }
+  SPW_CUDA(cudaStreamSynchronize(st));
+  return SPW_OK;
+}
+
 int spw_cov_p(const int* type, const int* n, const double* coords, const double* phi, const double* sig2, double* out,
               int* status) {
   const int rc = spw_cov(*type, *n, coords, *phi, *sig2, out);

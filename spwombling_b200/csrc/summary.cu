@@ -103,6 +103,36 @@ int transpose_batched(int rows, int cols, const double* in, long long in_ld, lon
   return SPW_OK;
 }
 
+// Posterior surface analysis of README.md:123-137: per (sample, grid point) the Hessian [[s11, s12], [s12, s22]] of the
+// drawn curvature gives det, the two eigenvalues (decreasing, as eigen() returns them), the Laplacian, and the
+// divergence s1 + s2.  draws / out: [S][5][G].
+__global__ void __launch_bounds__(256)
+surface_kernel(long long S, int G, const double* __restrict__ draws, double* __restrict__ out) {
+  const long long total = S * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / G;
+    const int g = (int)(i % G);
+    const double* d = draws + s * 5 * G + g;
+    const double s1 = d[0], s2 = d[G], a = d[2 * (long long)G], b = d[3 * (long long)G], c = d[4 * (long long)G];
+    const double t = 0.5 * (a + c), h = hypot(0.5 * (a - c), b);
+    double* o = out + s * 5 * G + g;
+    o[0] = a * c - b * b;            // det(hess.mat)
+    o[G] = t + h;                    // eigen(hess.mat)$values[1]
+    o[2 * (long long)G] = t - h;     // eigen(hess.mat)$values[2]
+    o[3 * (long long)G] = a + c;     // sum(diag(hess.mat))
+    o[4 * (long long)G] = s1 + s2;   // divergence
+  }
+}
+
+int surface_analysis_dev(int S, int G, const double* draws_dev, double* out_dev, cudaStream_t st) {
+  if (S <= 0 || G <= 0) return SPW_OK;
+  const long long total = (long long)S * G;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  surface_kernel<<<grid, 256, 0, st>>>(S, G, draws_dev, out_dev);
+  SPW_LAUNCHED();
+  return SPW_OK;
+}
+
 std::vector<int> batch_starts(int S, int nbatch) {
   // split(ngrad, ceiling(seq_along(ngrad) / (length(ngrad)/nbatch)))  -- R/spatial_gradient.R:392, in double arithmetic
   std::vector<int> starts;

@@ -280,3 +280,70 @@ def test_hlm_defaults_and_graph_equivalence(spw, monkeypatch):
     b = spw.hlmBayes_sp(**kw)
     for key in ("sig2", "tau2", "phi"):
         assert np.array_equal(a[key], b[key])
+
+
+# ---- workspace planning: batching over samples and chunking over the grid change no arithmetic ---------------
+def test_workspace_chunking_bit_identical(spw):
+    coords, grid, phi, sig2, z, eps = synth(300, 9, 21, "matern2", (15, 40), seed=33)      # G = 81, S = 21
+    model = {"phi": phi, "sig2": sig2, "z": z}
+    lib = spw.load()
+    full = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=3, eps=eps, return_moments=True, rounded=False)
+    try:
+        # ~6 MB: forces several sample batches AND several grid chunks (per sample: 2 x 300 x 304 x 8 B of factors
+        # plus 5 x 304 x 8 B per grid point)
+        lib.spw_set_workspace_limit(6 << 20)
+        small = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=3, eps=eps, return_moments=True,
+                                     rounded=False)
+    finally:
+        lib.spw_set_workspace_limit(0)
+    for k in full:
+        assert np.array_equal(full[k], small[k]), k
+
+
+def test_argument_errors(spw):
+    coords, grid, phi, sig2, z, eps = synth(50, 3, 4, "matern2", (10, 30), seed=1)
+    with pytest.raises(ValueError):
+        spw.spatial_gradient(coords, {"phi": phi, "sig2": sig2[:2], "z": z}, "matern2", grid, nbatch=2, eps=eps)
+    with pytest.raises(ValueError):
+        spw.spatial_gradient(coords, {"phi": phi, "sig2": sig2, "z": z}, "matern", grid, nbatch=2, eps=eps)
+    with pytest.raises(ValueError):        # coda::HPDinterval needs more than one batch median
+        spw.spatial_gradient(coords, {"phi": phi, "sig2": sig2, "z": z}, "matern2", grid, nbatch=1, eps=eps)
+
+
+# ---- posterior surface analysis (README.md:123-177) -------------------------------------------
+def test_surface_analysis(spw):
+    from oracle.surface import surface_analysis as oracle_surface
+    rng = np.random.default_rng(4)
+    S, G = 60, 23
+    est = {"grad.%s.mcmc" % k: rng.standard_normal((S, G)) * sc for k, sc in
+           zip(("s1", "s2", "s11", "s12", "s22"), (3, 3, 40, 25, 40))}
+    got = spw.surface_analysis(est, nbatch=10, return_mcmc=True)
+    ref = oracle_surface(*(est["grad.%s.mcmc" % k] for k in ("s1", "s2", "s11", "s12", "s22")), nbatch=10)
+    for name in ("det", "eigen1", "eigen2", "laplace", "div"):
+        scale = np.abs(ref[name + ".mcmc"]).max()
+        assert np.max(np.abs(got[name + ".mcmc"] - ref[name + ".mcmc"])) < 1e-12 * max(scale, 1.0) * 50
+        np.testing.assert_allclose(got[name][:, :3], ref[name][:, :3], rtol=1e-11, atol=1e-11 * scale)
+        assert np.array_equal(got[name][:, 3], ref[name][:, 3])
+
+
+# ---- bayes_cwomb(type = "riemann.sum") rides on spatial_gradient (R/spatial_wombling.R:114-157, :245-306) --------
+@pytest.mark.parametrize("cov_type,phir", [("matern2", (10, 30)), ("matern1", (3, 10))])
+def test_bayes_cwomb_riemann(spw, cov_type, phir):
+    from oracle.wombling import bayes_cwomb as oracle_cwomb
+    rng = np.random.Generator(np.random.Philox(12))
+    n, S = 120, 40
+    coords = rng.random((n, 2))
+    t = np.linspace(0.15, 0.85, 9)
+    curve = np.column_stack([t, 0.5 + 0.25 * np.sin(2 * np.pi * t)])
+    c = ncomp_of(cov_type)
+    model = {"phi": rng.uniform(*phir, S), "sig2": rng.uniform(0.5, 2, S), "z": rng.standard_normal((S, n))}
+    eps = rng.standard_normal((S, curve.shape[0], c))
+    got = spw.bayes_cwomb(coords=coords, model=model, cov_type=cov_type, nbatch=8, curve=curve, type="riemann.sum",
+                          eps=eps, rounded=False)
+    ref = oracle_cwomb(coords, model, cov_type, 8, curve, eps, rounded=False)
+    assert list(got) == list(ref)
+    for k in ref:
+        scale = max(np.abs(ref[k]).max(), 1.0)
+        assert np.max(np.abs(np.asarray(got[k]) - ref[k])) < 1e-9 * scale, k
+    with pytest.raises(NotImplementedError):
+        spw.bayes_cwomb(coords=coords, model=model, cov_type=cov_type, nbatch=8, curve=curve, type="rectilinear")
