@@ -4,7 +4,7 @@
 (``include/spwombling.h``, ``spwombling_b200/csrc``) with this Python mirror of the R interface on top.
 """
 from .api import (COV_TYPES, bayes_cwomb, chol, cov_gaussian, cov_matern1, cov_matern2, cov_matrix, cross_cov,  # noqa: F401
-                  hlmBayes_sp, hpd_summary, launch_count, ncomp_of, spatial_gradient, spsample,
+                  hlmBayes_sp, hlm_summary, hpd_summary, launch_count, ncomp_of, spatial_gradient, spsample,
                   surface_analysis)
 from ._lib import LIB_PATH, NotPositiveDefinite, SpwError, load  # noqa: F401
 

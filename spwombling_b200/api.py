@@ -327,6 +327,23 @@ def bayes_cwomb(coords=None, model=None, cov_type=None, nbatch=None, curve=None,
     return out
 
 
+def hlm_summary(sig2=None, tau2=None, phi=None, beta=None, z=None):
+    """Posterior medians and 95 % HPD intervals of the parameters and of every latent z column --
+    R/hlm_summary.R:19-50.  The O(S N) order statistics run through the same GPU reducer as the gradient summary
+    (``coda::HPDinterval`` on the raw samples = one sample per batch).  Returns ``{"param": rows (median, lower.hpd,
+    upper.hpd) for sig2, tau2, phi, beta..., "z": N x 4 (median, lower.hpd, upper.hpd, sig)}``."""
+    def one(x):
+        x = np.asarray(x, dtype=np.float64)
+        x = x.reshape(x.shape[0], -1)
+        return hpd_summary(x, x.shape[0])
+    rows = [one(sig2)[0], one(tau2)[0], one(phi)[0]]                       # R/hlm_summary.R:26-28
+    b = one(beta)
+    rows.extend(b)                                                          # :29 / :37
+    zest = one(z)                                                           # :41
+    sig = np.where(zest[:, 1] > 0, 1.0, np.where(zest[:, 2] < 0, -1.0, 0.0))   # :43-47
+    return {"param": np.vstack(rows), "z": np.column_stack([zest, sig])}
+
+
 SURFACE_NAMES = ("det", "eigen1", "eigen2", "laplace", "div")
 
 

@@ -781,10 +781,16 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
       return rcs[d];
     }
   if (!want_draws) return SPW_OK;
-  // the one gather: peer copies of the shards into the root's buffer (R/spatial_gradient.R:378-390 rbind)
+  // the one gather: peer copies of the shards into the root's buffer (R/spatial_gradient.R:378-390 rbind);
+  // with peer access enabled the copies go device to device over NVLink instead of staging through the host
   for (int d = 0; d < ngpu; ++d) {
     const int dev = (ngpu > 1) ? d : root;
     if (dev == root) continue;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, root, dev) == cudaSuccess && can) {
+      cudaError_t pe = cudaDeviceEnablePeerAccess(dev, 0);
+      if (pe != cudaSuccess) cudaGetLastError();   // already enabled (or unsupported): the copy still works
+    }
     const size_t cnt = (size_t)(lo_of(d + 1) - lo_of(d)) * g * c;
     SPW_CUDA(cudaMemcpyPeerAsync(dall.as<double>() + (size_t)lo_of(d) * g * c, root, results[d].draws.p, dev,
                                  sizeof(double) * cnt, rst));

@@ -347,3 +347,21 @@ def test_bayes_cwomb_riemann(spw, cov_type, phir):
         assert np.max(np.abs(np.asarray(got[k]) - ref[k])) < 1e-9 * scale, k
     with pytest.raises(NotImplementedError):
         spw.bayes_cwomb(coords=coords, model=model, cov_type=cov_type, nbatch=8, curve=curve, type="rectilinear")
+
+
+def test_hlm_summary(spw):
+    """R/hlm_summary.R:19-50: medians + coda::HPDinterval on the raw samples."""
+    from oracle.summary import hpd_interval
+    rng = np.random.default_rng(8)
+    S, n = 400, 17
+    sig2, tau2, phi = rng.gamma(2, 1, S), rng.gamma(3, 0.5, S), rng.uniform(1, 5, S)
+    beta = rng.standard_normal((S, 2))
+    z = rng.standard_normal((S, n)) + np.linspace(-1, 1, n)
+    got = spw.hlm_summary(sig2=sig2, tau2=tau2, phi=phi, beta=beta, z=z)
+    cols = [sig2, tau2, phi, beta[:, 0], beta[:, 1]]
+    for r, x in enumerate(cols):
+        lo, hi = hpd_interval(x[:, None])
+        np.testing.assert_allclose(got["param"][r], [np.median(x), lo[0], hi[0]], rtol=0, atol=0)
+    lo, hi = hpd_interval(z)
+    np.testing.assert_allclose(got["z"][:, :3], np.column_stack([np.median(z, axis=0), lo, hi]), rtol=0, atol=0)
+    assert set(np.unique(got["z"][:, 3])) <= {-1.0, 0.0, 1.0}
