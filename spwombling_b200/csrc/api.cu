@@ -95,6 +95,7 @@ struct DeviceCtx {
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
   size_t ws2_bytes = 0;
+  Lookahead la;                // second stream + events of the single-matrix Cholesky's lookahead schedule
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_ctx_mu;
@@ -106,6 +107,29 @@ static int get_ctx(DeviceCtx** out) {
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   if (!c.stream) SPW_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   *out = &c;
+  return SPW_OK;
+}
+
+// lookahead resources for factorising one matrix of order n (nullptr when disabled by SPW_LOOKAHEAD=0)
+static int get_lookahead(DeviceCtx& c, int n, Lookahead** out) {
+  *out = nullptr;
+  const char* env = getenv("SPW_LOOKAHEAD");
+  if (!(env && env[0] == '1')) return SPW_OK;   // opt-in until verified on the GPU
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (!c.la.bulk) {
+    int lo = 0, hi = 0;
+    SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SPW_CUDA(cudaStreamCreateWithPriority(&c.la.bulk, cudaStreamNonBlocking, lo));   // lowest priority: bulk work
+  }
+  const size_t need = (size_t)ceil_div(n, OUTER_W) + 1;
+  while (c.la.ev_chain.size() < need) {
+    cudaEvent_t a, b;
+    SPW_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    SPW_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    c.la.ev_chain.push_back(a);
+    c.la.ev_bulk.push_back(b);
+  }
+  *out = &c.la;
   return SPW_OK;
 }
 
@@ -466,6 +490,12 @@ int spw_shutdown(void) {
     c.ws2_bytes = 0;
     if (c.stream) cudaStreamDestroy(c.stream);
     c.stream = nullptr;
+    if (c.la.bulk) cudaStreamDestroy(c.la.bulk);
+    c.la.bulk = nullptr;
+    for (auto e : c.la.ev_chain) cudaEventDestroy(e);
+    for (auto e : c.la.ev_bulk) cudaEventDestroy(e);
+    c.la.ev_chain.clear();
+    c.la.ev_bulk.clear();
   }
   cudaSetDevice(cur);
   return SPW_OK;
@@ -555,7 +585,9 @@ int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) 
   SPW_CUDA(cudaMemcpy2DAsync(dm.p, sizeof(double) * ld, a, sizeof(double) * n, sizeof(double) * n, n,
                              cudaMemcpyHostToDevice, st));
   MatView L{dm.as<double>(), ld, (long long)n * ld};
-  SPW_TRY(potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st));
+  Lookahead* la;
+  SPW_TRY(get_lookahead(*ctx, n, &la));
+  SPW_TRY(potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st, la));
   SPW_TRY(logdet_quad_batched(n, L, dl.as<double>(), nullptr, 1, st));
   std::vector<double> tmp((size_t)n * n);
   int status = 0;
@@ -624,6 +656,7 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   ws.status = ds.as<int>();
   ws.state = (HlmState*)dstate.p;
   ws.plan = plan;
+  SPW_TRY(get_lookahead(*ctx, n, &ws.la));
   int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
                        b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
                        o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);

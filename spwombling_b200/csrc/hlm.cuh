@@ -14,6 +14,7 @@ struct HlmWorkspace {
   int* status = nullptr;
   HlmState* state = nullptr;
   const LinalgPlan* plan = nullptr;   // built with extra_rows = 1
+  Lookahead* la = nullptr;            // optional lookahead schedule of the Cholesky
 };
 
 size_t hlm_state_bytes();

@@ -468,6 +468,8 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   plan.panel.resize(plan.nblk);
   plan.trail.resize(plan.nblk);
   plan.outer.clear();
+  plan.outer_next.clear();
+  plan.outer_bulk.clear();
   int pm, pn, im, in_, om, on;
   shape_dims(plan.shape_panel, pm, pn);
   shape_dims(plan.shape_inner, im, in_);
@@ -508,23 +510,33 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
       }
       plan.trail[j].count = (int)tasks.size() - plan.trail[j].begin;
     }
-    // outer trailing update: C[I][K] -= L[I][J0:J1] * L[K][J0:J1]^T for the lower triangle right of the outer block
-    ChunkRange o;
-    o.begin = (int)tasks.size();
-    for (int r = J1; r < plan.rows; r += om) {
-      const int m = std::min(om, plan.rows - r);
-      for (int c = J1; c < n && c <= r + m - 1; c += on) {
-        GemmTask t = blank_task();
-        t.a_row = r; t.a_col = J0;
-        t.b_row = c; t.b_col = J0;
-        t.c_row = r; t.c_col = c;
-        t.m = m; t.n = std::min(on, n - c); t.k = J1 - J0;
-        t.flags = GT_ACCUM | GT_STORE;
-        tasks.push_back(t);
+    // outer trailing update: C[I][K] -= L[I][J0:J1] * L[K][J0:J1]^T for the lower triangle right of the outer block;
+    // listed as two consecutive groups -- the columns of the NEXT outer block first (what the next panel needs), then
+    // the rest (the bulk a lookahead schedule runs concurrently with the next panel)
+    ChunkRange o, oa, ob;
+    o.begin = oa.begin = (int)tasks.size();
+    for (int part = 0; part < 2; ++part) {
+      if (part == 1) ob.begin = (int)tasks.size();
+      for (int r = J1; r < plan.rows; r += om) {
+        const int m = std::min(om, plan.rows - r);
+        for (int c = J1; c < n && c <= r + m - 1; c += on) {
+          if ((c < J1 + OUTER_W) != (part == 0)) continue;
+          GemmTask t = blank_task();
+          t.a_row = r; t.a_col = J0;
+          t.b_row = c; t.b_col = J0;
+          t.c_row = r; t.c_col = c;
+          t.m = m; t.n = std::min(on, n - c); t.k = J1 - J0;
+          t.flags = GT_ACCUM | GT_STORE;
+          tasks.push_back(t);
+        }
       }
+      if (part == 0) oa.count = (int)tasks.size() - oa.begin;
     }
+    ob.count = (int)tasks.size() - ob.begin;
     o.count = (int)tasks.size() - o.begin;
     plan.outer.push_back(o);
+    plan.outer_next.push_back(oa);
+    plan.outer_bulk.push_back(ob);
   }
   // triangular inverse levels: s = NB, 2NB, ... ; pairs (block1 = [o, o+s), block2 = [o+s, min(o+2s, n)))
   for (int s = NB; s < n; s *= 2) {
@@ -603,17 +615,21 @@ struct Operand {
   int rows, cols;
 };
 
+// one_per_sm: pad the dynamic shared memory so that only one CTA fits per SM (leaves room for the CTAs of a
+// concurrently running latency-critical kernel)
 template <class Cfg>
 static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C, MatView CT,
-                           double alpha, cudaStream_t st) {
+                           double alpha, cudaStream_t st, bool one_per_sm) {
   if (count <= 0 || batch <= 0) return SPW_OK;
   static bool attr_set[64] = {false};
   int dev = 0;
   SPW_CUDA(cudaGetDevice(&dev));
+  const size_t smem_wide = std::max<size_t>(Cfg::SMEM, 117 * 1024);   // two such CTAs exceed the 228 KB of an SM
   if (!attr_set[dev & 63]) {
-    SPW_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    SPW_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide));
     attr_set[dev & 63] = true;
   }
+  const size_t smem = one_per_sm ? smem_wide : Cfg::SMEM;
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     const int nb = std::min(65535, batch - b0);
     MatView a = A.v, b = B.v, c = C, ct = CT;
@@ -624,7 +640,7 @@ static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand 
     CUtensorMap tmA, tmB;
     SPW_TRY(make_tensor_map(&tmA, a, A.cols, A.rows, nb, G_LDS, Cfg::BM));
     SPW_TRY(make_tensor_map(&tmB, b, B.cols, B.rows, nb, G_LDS, Cfg::BN));
-    gemm_tma_kernel<Cfg><<<dim3(count, nb), G_THREADS, Cfg::SMEM, st>>>(tmA, tmB, tasks, c, ct, alpha);
+    gemm_tma_kernel<Cfg><<<dim3(count, nb), G_THREADS, smem, st>>>(tmA, tmB, tasks, c, ct, alpha);
     SPW_LAUNCHED();
   }
   return SPW_OK;
@@ -632,16 +648,16 @@ static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand 
 
 // shape: 0 = L (128 x 128), 1 = M (128 x 64), 2 = S (64 x 64); the task list must have been tiled accordingly
 static int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
-                             MatView CT, double alpha, cudaStream_t st) {
+                             MatView CT, double alpha, cudaStream_t st, bool one_per_sm = false) {
   switch (shape) {
-    case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st);
-    case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st);
-    default: return launch_gemm_cfg<GCfgS>(tasks, count, batch, A, B, C, CT, alpha, st);
+    case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
+    case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
+    default: return launch_gemm_cfg<GCfgS>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
   }
 }
 
 int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv, int batch, int* status,
-                  cudaStream_t st) {
+                  cudaStream_t st, Lookahead* la) {
   MatView dv{dinv, NB, (long long)plan.nblk * NB * NB};
   MatView none{nullptr, 0, 0};
   MatView lv = linv ? *linv : none;
@@ -655,6 +671,8 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     diag_attr[dev & 63] = true;
   }
   const int per_outer = OUTER_W / NB;
+  const int nouter = (int)plan.outer.size();
+  const bool ahead = la && la->bulk && (int)la->ev_chain.size() >= nouter && (int)la->ev_bulk.size() >= nouter && nouter > 2;
   for (int j = 0; j < plan.nblk; ++j) {
     diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
                                                                g_diag_dbg);
@@ -664,10 +682,29 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
                               L, none, -1.0, st));
     if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
-      const ChunkRange& o = plan.outer[j / per_outer];
-      SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
+      const int m = j / per_outer;
+      if (!ahead) {
+        const ChunkRange& o = plan.outer[m];
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
+      } else {
+        // Lookahead: the panel of outer block m is final.  The bulk of its trailing update (columns beyond the next
+        // outer block) goes to the second stream, one CTA per SM so that the CTAs of the next panel's small kernels
+        // find room at once; the main stream only updates the next outer block's columns and moves on to its panel.
+        //   bulk(m)  waits for: panel m (ev_chain[m]) and bulk(m-1) (stream order)
+        //   next(m)  waits for: bulk(m-1) (ev_bulk[m-1]): it touches columns bulk(m-1) also updates
+        const ChunkRange& oa = plan.outer_next[m];
+        const ChunkRange& ob = plan.outer_bulk[m];
+        SPW_CUDA(cudaEventRecord(la->ev_chain[m], st));
+        SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[m], 0));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
+                                  la->bulk, true));
+        SPW_CUDA(cudaEventRecord(la->ev_bulk[m], la->bulk));
+        if (m > 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[m - 1], 0));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+      }
     }
   }
+  if (ahead) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[nouter - 1], 0));   // join
   return SPW_OK;
 }
 

@@ -37,6 +37,7 @@ struct LinalgPlan {
   int shape_panel = 1, shape_inner = 1, shape_outer = 1;   // GEMM tile shapes (0: 128x128, 1: 128x64, 2: 64x64)
   std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
   std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
+  std::vector<ChunkRange> outer_next, outer_bulk;   // the same tasks split: next outer block's columns / the rest
   std::vector<ChunkRange> inv1, inv2;           // per trtri level
   ChunkRange prod{0, 0};                        // T^T T of an inverted factor (spsample)
   GemmTask* d_tasks = nullptr;
@@ -54,8 +55,13 @@ void plan_free(LinalgPlan& plan);
 // for the inverted diagonal blocks.  linv (optional): receives the inverted diagonal blocks (lower part
 // and mirrored upper part) as the level-0 state of the triangular inverse.
 // status[b] is set to the (1-based) order of the first non-positive leading minor, 0 if none.
+// Optional lookahead schedule (single-matrix chains): a second stream and per-outer-block events.
+struct Lookahead {
+  cudaStream_t bulk = nullptr;
+  std::vector<cudaEvent_t> ev_chain, ev_bulk;
+};
 int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv, int batch, int* status,
-                  cudaStream_t st);
+                  cudaStream_t st, Lookahead* la = nullptr);
 
 // Batched inverse of the lower-triangular factor: on exit the lower triangle of linv holds L^-1 and the
 // upper triangle its transpose.  Uses the strict upper triangle of L as scratch.  Requires the
