@@ -18,6 +18,7 @@ struct HlmWorkspace {
 };
 
 size_t hlm_state_bytes();
+constexpr int HLM_SMALL_MAX = 175;   // largest n handled by the single-CTA register-resident chain (n + 1 <= 16 * 11)
 
 // All pointers are device pointers except info_host.  Outputs as documented for spw_hlm_run.
 int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const double* cy, const double* y_dev,

@@ -4,6 +4,7 @@
 //   chol()      R/hlmBayes_sp.R:99,114,140,181; R/spatial_gradient.R:216,265,304   (dpotrf)
 //   chol2inv()  same lines (dpotri) -- not formed: K^-1 = Linv^T Linv is applied through Linv only.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "linalg.cuh"
 #include "tma.cuh"
@@ -696,8 +697,9 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
         const ChunkRange& ob = plan.outer_bulk[m];
         SPW_CUDA(cudaEventRecord(la->ev_chain[m], st));
         SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[m], 0));
+        static const bool bulk_one_per_sm = !(getenv("SPW_LA_WIDE") && getenv("SPW_LA_WIDE")[0] == '0');
         SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
-                                  la->bulk, true));
+                                  la->bulk, bulk_one_per_sm));
         SPW_CUDA(cudaEventRecord(la->ev_bulk[m], la->bulk));
         if (m > 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[m - 1], 0));
         SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
