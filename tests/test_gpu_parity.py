@@ -365,3 +365,26 @@ def test_hlm_summary(spw):
     lo, hi = hpd_interval(z)
     np.testing.assert_allclose(got["z"][:, :3], np.column_stack([np.median(z, axis=0), lo, hi]), rtol=0, atol=0)
     assert set(np.unique(got["z"][:, 3])) <= {-1.0, 0.0, 1.0}
+
+
+# ---- opt-in schedules give the same results as the default ones ---------------------------------------------------
+def test_hlm_opt_in_paths(spw, monkeypatch):
+    rng = np.random.Generator(np.random.Philox(77))
+    n, niter = 90, 30
+    coords = rng.random((n, 2))
+    y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
+    kw = dict(y=y, coords=coords, niter=niter, nburn=10, report=10, cov_type="matern2",
+              norm=rng.standard_normal(3 * niter), unif=rng.random(3 * niter), trgtFn_compute=True, verbose=False)
+    base = spw.hlmBayes_sp(**kw)
+    monkeypatch.setenv("SPW_HLM_SMALL", "1")          # single-CTA register-resident chain (n <= 175)
+    small = spw.hlmBayes_sp(**kw)
+    monkeypatch.delenv("SPW_HLM_SMALL")
+    for key in ("sig2", "tau2", "phi", "trgt_fn"):
+        np.testing.assert_allclose(small[key], base[key], rtol=1e-10)
+    np.testing.assert_array_equal(small["diagnostics"]["accept_m"], base["diagnostics"]["accept_m"])
+    monkeypatch.setenv("SPW_LOOKAHEAD", "1")          # two-stream lookahead in the single-matrix Cholesky
+    A = oracle.cov_matern2(oracle.dist_matrix(rng.random((900, 2))), 6.0, 1.3) + 0.7 * np.eye(900)
+    U1, l1 = spw.chol(A)
+    monkeypatch.delenv("SPW_LOOKAHEAD")
+    U0, l0 = spw.chol(A)
+    assert np.array_equal(U0, U1) and l0 == l1
