@@ -35,6 +35,11 @@ WORKLOADS = {
     # BASELINE.json configs[3]
     "c4": dict(name="C4: synthetic N=2000 uniform coords, gaussian, 60x60 grid", n=2000, cov="gaussian", gside=60,
                phi=(3000.0, 6000.0), batch=64, g_cpu=32),
+    # BASELINE.json configs[1] / configs[2] at their sizes (synthetic coordinates; the real datasets are test fixtures)
+    "c2": dict(name="C2-size: N=155 (meuse), matern1, 50x50 grid", n=155, cov="matern1", gside=50,
+               phi=(2.0, 8.0), batch=1000, g_cpu=2500),
+    "c3": dict(name="C3-size: N=506 (boston.c), matern2, 134 grid points (12x12 here)", n=506, cov="matern2", gside=12,
+               phi=(30.0, 60.0), batch=1000, g_cpu=144),
     # BASELINE.json configs[0] (README synthetic)
     "c1": dict(name="C1: README synthetic N=100, matern2, 19x19 grid", n=100, cov="matern2", gside=19,
                phi=(10.0, 30.0), batch=1000, g_cpu=361),
