@@ -388,3 +388,37 @@ def test_hlm_opt_in_paths(spw, monkeypatch):
     monkeypatch.delenv("SPW_LOOKAHEAD")
     U0, l0 = spw.chol(A)
     assert np.array_equal(U0, U1) and l0 == l1
+
+
+# ---- edge shapes of the fused kernel: N a multiple of the 128-row block (no ragged block), tiny / ragged grids -----
+@pytest.mark.parametrize("n,G,cov_type,phir", [(128, 1, "matern2", (10, 30)), (256, 17, "matern2", (15, 40)),
+                                               (384, 33, "matern1", (20, 40)), (127, 16, "gaussian", (80, 160)),
+                                               (129, 31, "matern2", (10, 30)), (3, 2, "matern2", (2, 4))])
+def test_gradient_edge_shapes(spw, n, G, cov_type, phir):
+    rng = np.random.Generator(np.random.Philox(n * 1000 + G))
+    coords = rng.random((n, 2))
+    grid = rng.random((G, 2))
+    S = 3
+    c = ncomp_of(cov_type)
+    phi, sig2 = rng.uniform(*phir, S), rng.uniform(0.5, 2, S)
+    z = rng.standard_normal((S, n))
+    eps = rng.standard_normal((S, G, c))
+    want_d, want_m, want_v = gradient_draws(coords, grid, cov_type, phi, sig2, z, eps, want_moments=True)
+    out = spw.spatial_gradient(coords, {"phi": phi, "sig2": sig2, "z": z}, cov_type, grid, nbatch=3, eps=eps,
+                               return_moments=True, rounded=False)
+    names = ("s1", "s2", "s11", "s12", "s22")[:c]
+    got_d = np.stack([out["grad.%s.mcmc" % nm] for nm in names], axis=2)
+    assert rel_err(out["mean.grad"], want_m, axis=2) < RTOL
+    assert rel_err(out["var.grad"].reshape(S, -1, c * c), want_v.reshape(S, -1, c * c), axis=2) < RTOL
+    assert rel_err(got_d, want_d, axis=2) < RTOL
+
+
+def test_gradient_kernel_variants_agree(spw, monkeypatch):
+    """The cp.async / __syncthreads kernel (SPW_MAIN=0) and the default TMA kernel compute the same quantities."""
+    coords, grid, phi, sig2, z, eps = synth(300, 5, 4, "matern2", (15, 40), seed=3)
+    model = {"phi": phi, "sig2": sig2, "z": z}
+    tma = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=2, eps=eps, return_moments=True, rounded=False)
+    monkeypatch.setenv("SPW_MAIN", "0")
+    old = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=2, eps=eps, return_moments=True, rounded=False)
+    assert rel_err(tma["mean.grad"], old["mean.grad"], axis=2) < 1e-12
+    assert rel_err(tma["var.grad"].reshape(4, -1, 25), old["var.grad"].reshape(4, -1, 25), axis=2) < 1e-12
