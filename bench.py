@@ -201,15 +201,11 @@ def run_ours(args, w):
         return mine
 
     def step_e2e(i):
-        h = host[i % npool]
-        d = {k: v.to(device, non_blocking=True) for k, v in h.items()}
-        mine = dev.gradient_shard(coords_d, grid_d, cov, d["phi"], d["sig2"], d["z"], d["eps"], out=draws_buf)
-        full = dev.gather_shards(mine, B * world) if world > 1 else mine
-        if rank == 0:
-            summ = dev.hpd_summary_dev(full, nbatch_sum).cpu()
-            draws_r = dev.draws_to_r_layout(full).cpu()
-            return summ, draws_r
-        return None
+        # the public multi-rank entry point: pinned host shard in, the reference's list (estimates + draws) out on rank 0
+        h = dict(host[i % npool])
+        h["S_total"] = B * world
+        return dev.spatial_gradient_sharded(coords, None, cov, grid, nbatch=nbatch_sum, return_mcmc=True, local=h,
+                                            device=device, rounded=False)
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -250,7 +246,7 @@ def run_ours(args, w):
     # ---- e2e: pinned host inputs -> H2D -> shard -> gather -> summary + draws -> D2H ----
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(int(v.numel()) * 8 for v in host[0].values())
+    h2d = sum(int(v.numel()) * 8 for v in host[0].values()) + (coords.size + grid.size) * 8
     d2h = (c * 3 * G + B * world * c * G) * 8
     if rank != 0:
         if world > 1:

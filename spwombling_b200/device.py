@@ -113,11 +113,13 @@ def gather_shards(mine, S, group=None):
 
 def spatial_gradient_sharded(coords, model, cov_type, grid_points, nbatch=200, return_mcmc=True, eps=None,
                              group=None, device=None, rounded=True, prob=0.95,
-                             compute=None, summarise=None, to_r_layout=None):
+                             compute=None, summarise=None, to_r_layout=None, local=None):
     """``spatial_gradient`` over the ranks of a torch.distributed process group (one process per GPU).
 
     Every rank passes the full host inputs and works on its ``shard_bounds`` range; rank 0 returns the
-    reference's list as a dict, the other ranks return None.  ``compute`` / ``summarise`` / ``to_r_layout``
+    reference's list as a dict, the other ranks return None.  Alternatively ``local`` hands over this rank's shard
+    directly: a dict of (pinned) host tensors ``phi, sig2, z, eps`` covering exactly ``shard_bounds(S_total, ...)``
+    plus ``S_total`` (``model`` / ``eps`` are then ignored).  ``compute`` / ``summarise`` / ``to_r_layout``
     default to the CUDA entry points (they exist as arguments so that the host logic -- sharding, gather,
     assembly -- can be exercised on CPU with the gloo backend in the tests).
     """
@@ -134,18 +136,25 @@ def spatial_gradient_sharded(coords, model, cov_type, grid_points, nbatch=200, r
     coords_d = coords_to_device(coords, device)
     grid_d = coords_to_device(grid_points, device)
     n, g = coords_d.shape[1], grid_d.shape[1]
-    phi = np.asarray(model["phi"], dtype=np.float64).reshape(-1)
-    S = phi.shape[0]
-    lo, hi = shard_bounds(S, world, rank)
-    sl = slice(lo, hi)
-
     def up(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device, non_blocking=True)
 
-    phi_d = up(phi[sl])
-    sig2_d = up(np.asarray(model["sig2"], dtype=np.float64).reshape(-1)[sl])
-    z_d = up(np.asarray(model["z"], dtype=np.float64).reshape(S, n)[sl])
-    eps_d = up(np.asarray(eps, dtype=np.float64).reshape(S, g, c)[sl])
+    if local is not None:
+        S = int(local["S_total"])
+        lo, hi = shard_bounds(S, world, rank)
+        phi_d, sig2_d, z_d, eps_d = up(local["phi"]), up(local["sig2"]), up(local["z"]), up(local["eps"])
+        if phi_d.shape[0] != hi - lo:
+            raise ValueError("local shard must hold exactly the samples of shard_bounds(S_total, world, rank)")
+    else:
+        phi = np.asarray(model["phi"], dtype=np.float64).reshape(-1)
+        S = phi.shape[0]
+        lo, hi = shard_bounds(S, world, rank)
+        sl = slice(lo, hi)
+        phi_d = up(phi[sl])
+        sig2_d = up(np.asarray(model["sig2"], dtype=np.float64).reshape(-1)[sl])
+        z_d = up(np.asarray(model["z"], dtype=np.float64).reshape(S, n)[sl])
+        eps_d = up(np.asarray(eps, dtype=np.float64).reshape(S, g, c)[sl])
     mine = compute(coords_d, grid_d, cov_type, phi_d, sig2_d, z_d, eps_d)
     draws_all = gather_shards(mine, S, group) if multi else mine
     if rank != 0:
