@@ -72,6 +72,12 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # not built yet: build it in-tree if nvcc is here (this is a compile step, not a fallback path)
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "nvcc")):
+            from .build import build
+            build()
+    if not os.path.exists(LIB_PATH):
         raise ImportError("libspwombling.so not found at %s -- run `python -m spwombling_b200.build` "
                           "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
