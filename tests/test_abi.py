@@ -58,3 +58,16 @@ def test_argument_errors_without_gpu(lib_path):
         api.cov_matrix([[0.0, 0.0]], "exponential", 1.0)      # only the three named kernels
     with pytest.raises(ValueError):
         api.hlmBayes_sp(y=[1.0, 2.0], coords=[[0, 0], [1, 1]], niter=10, cov_type="matern1", verbose=False)
+
+
+def test_r_glue_compiles_against_stub():
+    """r/src/r_glue.c cannot be built here (no R), but it must at least be valid C whose calls match the prototypes
+    of include/spwombling.h: compile it with -fsyntax-only against a minimal stand-in for R's headers."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    cmd = ["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tools", "r_stub"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "r_glue.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -117,3 +117,24 @@ def test_fullsize_cholesky_and_hlm_quantities(n):
                           unif=np.full(3, 0.5), trgtFn_compute=True, verbose=False)
     want_trgt = -(2 + 1) * 0.0 - 1.0 - -(2 + 1) * 0.0 - 1.0 - want_half / 4 - quad / 2
     assert out["trgt_fn"][0] == pytest.approx(want_trgt, rel=1e-10)
+
+
+def test_hlm_chain_blocked_path_vs_oracle():
+    """A chain at a size that exercises the multi-block Cholesky schedule (16 diagonal blocks, 4 outer blocks, the
+    appended y row) against the reference's explicit-inverse arithmetic."""
+    import spwombling_b200 as spw
+    from oracle.hlm import hlm_bayes_sp
+    n, niter = 1000, 6
+    rng = np.random.Generator(np.random.Philox(4242))
+    coords = rng.random((n, 2))
+    y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
+    y = y - y.mean()
+    norm, unif = rng.standard_normal(3 * niter), rng.random(3 * niter)
+    ref = hlm_bayes_sp(y, coords, niter=niter, nburn=2, report=3, cov_type="matern1", norm=norm, unif=unif,
+                       trgt_fn_compute=True)
+    out = spw.hlmBayes_sp(y=y, coords=coords, niter=niter, nburn=2, report=3, cov_type="matern1", norm=norm, unif=unif,
+                          trgtFn_compute=True, verbose=False)
+    for key in ("sig2", "tau2", "phi"):
+        np.testing.assert_allclose(out["diagnostics"]["chain"][key], ref["chain"][key], rtol=1e-10)
+    np.testing.assert_allclose(out["trgt_fn"], ref["trgt_fn"], rtol=1e-10)
+    np.testing.assert_array_equal(out["diagnostics"]["accept_m"], ref["accept_m"])
