@@ -673,15 +673,29 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
   }
   const int per_outer = OUTER_W / NB;
   const int nouter = (int)plan.outer.size();
+  // SPW_POTRF_PROFILE=1: CUDA-event timing of the four kinds of launches (diagnostic; serialises nothing extra)
+  static const bool prof = getenv("SPW_POTRF_PROFILE") && getenv("SPW_POTRF_PROFILE")[0] == '1';
+  std::vector<cudaEvent_t> evs;
+  auto mark = [&]() {
+    if (!prof) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    evs.push_back(e);
+  };
   const bool ahead = la && la->bulk && (int)la->ev_chain.size() >= nouter && (int)la->ev_bulk.size() >= nouter && nouter > 2;
   for (int j = 0; j < plan.nblk; ++j) {
+    mark();
     diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
                                                                g_diag_dbg);
     SPW_LAUNCHED();
+    mark();
     SPW_TRY(launch_gemm_tasks(plan.shape_panel, plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, opL, opD,
                               L, none, 1.0, st));
+    mark();
     SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
                               L, none, -1.0, st));
+    mark();
     if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
       const int m = j / per_outer;
       if (!ahead) {
@@ -707,6 +721,19 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     }
   }
   if (ahead) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[nouter - 1], 0));   // join
+  if (prof && !evs.empty()) {
+    mark();
+    cudaStreamSynchronize(st);
+    double t[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i + 1 < evs.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+      t[i % 4] += ms;   // diag, panel, inner, (outer + gap to the next diag)
+    }
+    fprintf(stderr, "[spw] potrf n=%d batch=%d: diag %.3f ms, panel %.3f ms, inner %.3f ms, outer %.3f ms\n", plan.n, batch,
+            t[0], t[1], t[2], t[3]);
+    for (auto e : evs) cudaEventDestroy(e);
+  }
   return SPW_OK;
 }
 
