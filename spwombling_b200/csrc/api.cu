@@ -227,8 +227,8 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   const size_t budget = reuse ? 0 : workspace_budget();
   int gc = std::min(G, 65535);
   int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / (per_sample_fixed + at_per_g * gc));
-  // beyond ~48 GB a larger batch buys no efficiency and only makes the allocation slow
-  const size_t soft_cap = (size_t)48 << 30;
+  // beyond ~24 GB a larger batch buys no efficiency and only makes the allocation slow
+  const size_t soft_cap = (size_t)24 << 30;
   if (B > 16 && (per_sample_fixed + at_per_g * gc) * (size_t)B > soft_cap)
     B = std::max<int>(16, (int)(soft_cap / (per_sample_fixed + at_per_g * gc)));
   if (reuse) {
