@@ -47,6 +47,10 @@ int spw_set_workspace_limit(long long bytes);
 /* number of CUDA kernel launches issued by this library since the last call with reset != 0 */
 long long spw_launch_count(int reset);
 
+/* 1 if the last multi-GPU spw_gradient_run gathered its shards with NCCL (grouped send/recv over NVLink; libnccl is
+ * dlopen()ed, SPW_NCCL=0 disables), 0 if it used peer copies, -1 if no multi-GPU gather has run yet */
+int spw_last_gather_used_nccl(void);
+
 /* Phase timing of the spatial_gradient pipeline with CUDA events on the launching stream (off by default).
  * ms / calls have 6 entries: 0 covariance assembly, 1 Cholesky, 2 triangular inverse, 3 Linv z,
  * 4 cross-covariance assembly, 5 fused TRMM + Gram + draw kernel; main_flops = algorithmic flops of phase 5
@@ -110,7 +114,8 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type,
  *   R/spatial_gradient.R:239-240) are optional (NULL to skip).
  *   ngpu >= 1: samples are sharded contiguously over the first ngpu devices of this process
  *   (R/spatial_gradient.R:29-32,200: mclapply over sample chunks), the shards' draws are gathered
- *   once on device 0 over NVLink peer copies, and summarised there. */
+ *   once on device 0 -- one grouped NCCL send/recv over NVLink (peer copies if libnccl cannot be loaded) --
+ *   and summarised there. */
 int spw_gradient_run(int type, int n, const double* coords, int g, const double* grid,
                      int S, const double* phi, const double* sig2, const double* z, const double* eps,
                      int ngpu, int nbatch, double prob,

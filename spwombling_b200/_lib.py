@@ -27,6 +27,7 @@ SIGNATURES = {
     "spw_shutdown": (c_int, []),
     "spw_set_workspace_limit": (c_int, [c_ll]),
     "spw_launch_count": (c_ll, [c_int]),
+    "spw_last_gather_used_nccl": (c_int, []),
     "spw_profile_enable": (c_int, [c_int]),
     "spw_profile_read": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "spw_debug_diag_timing": (c_int, [c_vp]),

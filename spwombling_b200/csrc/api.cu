@@ -4,6 +4,7 @@
 #include <ctime>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -388,6 +389,86 @@ static int spsample_shard(int type, int n, const double* cx, const double* cy, i
   return SPW_OK;
 }
 
+// ---- NCCL, loaded at run time (dlopen) so that the library links against libcudart only and never clashes with
+//      the copy of NCCL a host process (PyTorch) may already have mapped ------------------------------------------
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int g_last_gather_nccl = -1;   // 1: the last multi-GPU gather went through NCCL, 0: peer copies, -1: none yet
+static std::vector<NcclApi::comm_t> g_nccl_comms;   // communicator clique over devices 0 .. n-1 (cached)
+static std::mutex g_nccl_mu;
+
+static bool nccl_load() {
+  static bool tried = false;
+  if (tried) return g_nccl.ok;
+  tried = true;
+  const char* env = getenv("SPW_NCCL");
+  if (env && env[0] == '0') return false;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return false;
+  g_nccl.CommInitAll = (int (*)(NcclApi::comm_t*, int, const int*))dlsym(h, "ncclCommInitAll");
+  g_nccl.CommDestroy = (int (*)(NcclApi::comm_t))dlsym(h, "ncclCommDestroy");
+  g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, NcclApi::comm_t, cudaStream_t))dlsym(h, "ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, NcclApi::comm_t, cudaStream_t))dlsym(h, "ncclRecv");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Send &&
+              g_nccl.Recv;
+  return g_nccl.ok;
+}
+
+// The path's one exchange step as an NCCL collective over NVLink: every device d > 0 sends its [S_d][c][g] block,
+// device 0 receives them into the sample-major gather buffer (grouped ncclSend / ncclRecv, datatype ncclFloat64 = 8).
+// Returns SPW_OK, or a negative value when NCCL is unavailable (the caller then uses peer copies).
+static int nccl_gather(int ngpu, const std::vector<const double*>& src, const std::vector<size_t>& count,
+                       const std::vector<double*>& dst_on_root) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (!nccl_load()) return -1;
+  if ((int)g_nccl_comms.size() != ngpu) {
+    for (auto c : g_nccl_comms) g_nccl.CommDestroy(c);
+    g_nccl_comms.assign(ngpu, nullptr);
+    std::vector<int> devs(ngpu);
+    for (int d = 0; d < ngpu; ++d) devs[d] = d;
+    int rc = g_nccl.CommInitAll(g_nccl_comms.data(), ngpu, devs.data());
+    if (rc != 0) {
+      g_nccl_comms.clear();
+      return -1;
+    }
+  }
+  int rc = g_nccl.GroupStart();
+  for (int d = 1; d < ngpu && rc == 0; ++d) {
+    if (count[d] == 0) continue;
+    cudaSetDevice(0);
+    rc = g_nccl.Recv(dst_on_root[d], count[d], 8 /* ncclFloat64 */, d, g_nccl_comms[0], g_ctx[0].stream);
+    if (rc != 0) break;
+    cudaSetDevice(d);
+    rc = g_nccl.Send(src[d], count[d], 8, 0, g_nccl_comms[d], g_ctx[d].stream);
+  }
+  const int rc2 = g_nccl.GroupEnd();
+  cudaSetDevice(0);
+  if (rc != 0 || rc2 != 0) {
+    set_error("NCCL gather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc ? rc : rc2) : "?");
+    return SPW_ERR_CUDA;
+  }
+  for (int d = 1; d < ngpu; ++d) {       // the sends run on the senders' streams
+    cudaSetDevice(d);
+    if (cudaStreamSynchronize(g_ctx[d].stream) != cudaSuccess) return SPW_ERR_CUDA;
+  }
+  cudaSetDevice(0);
+  return SPW_OK;
+}
+
 // small RAII helper for temporary device buffers of the host-pointer entry points
 struct DevBuf {
   void* p = nullptr;
@@ -436,6 +517,8 @@ long long spw_launch_count(int reset) {
   if (reset) g_launches = 0;
   return v;
 }
+
+int spw_last_gather_used_nccl(void) { return g_last_gather_nccl; }
 
 int spw_profile_enable(int on) {
   g_profile = on;
@@ -818,9 +901,24 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
       return rcs[d];
     }
   if (!want_draws) return SPW_OK;
-  // the one gather: peer copies of the shards into the root's buffer (R/spatial_gradient.R:378-390 rbind);
-  // with peer access enabled the copies go device to device over NVLink instead of staging through the host
-  for (int d = 0; d < ngpu; ++d) {
+  // the one gather (R/spatial_gradient.R:378-390 rbind): a single grouped NCCL send/recv over NVLink when NCCL can
+  // be loaded, otherwise peer copies (device to device over NVLink once peer access is enabled)
+  bool gathered = (ngpu == 1);
+  if (!gathered) {
+    std::vector<const double*> src(ngpu, nullptr);
+    std::vector<size_t> cnt(ngpu, 0);
+    std::vector<double*> dst(ngpu, nullptr);
+    for (int d = 1; d < ngpu; ++d) {
+      src[d] = results[d].draws.as<double>();
+      cnt[d] = (size_t)(lo_of(d + 1) - lo_of(d)) * g * c;
+      dst[d] = dall.as<double>() + (size_t)lo_of(d) * g * c;
+    }
+    const int nrc = nccl_gather(ngpu, src, cnt, dst);
+    if (nrc == SPW_OK) gathered = true;
+    else if (nrc > 0) { free_shards(); return nrc; }
+    g_last_gather_nccl = gathered ? 1 : 0;
+  }
+  for (int d = 0; d < ngpu && !gathered; ++d) {
     const int dev = (ngpu > 1) ? d : root;
     if (dev == root) continue;
     int can = 0;
