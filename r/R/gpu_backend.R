@@ -55,3 +55,29 @@ spatial_gradient <- function(coords = NULL, model = NULL, cov.type = c("matern1"
   if (return.mcmc) for (k in seq_len(nc)) out[[paste0("grad.", comp[k], ".mcmc")]] <- res[[2]][, , k]
   out
 }
+
+spsample <- function(y = NULL, X = NULL, coords = NULL, phi = NULL, sig2 = NULL, tau2 = NULL,
+                     cov.type = c("matern1", "matern2", "gaussian"), silent = TRUE) {
+  if (is.null(cov.type)) stop("Please provide a covariance kernel!")                 # R/spsample_beta.R:27
+  N <- length(y); S <- length(phi); p <- ncol(X)
+  XtX <- t(X) %*% X                                                                   # :30
+  beta <- matrix(0, S, p); w <- matrix(0, N, S); eps <- matrix(0, N, S)
+  for (i in seq_len(S)) {                                                             # p x p block, :76-78, and the variates in
+    post_sd_beta <- chol2inv(chol(1e-4 * diag(p) + XtX / tau2[i]))                    # the reference's order: rnorm(p), rnorm(N)
+    post_mean_beta <- post_sd_beta %*% crossprod(X, y - mean(y)) / tau2[i]
+    beta[i, ] <- as.vector(crossprod(chol(post_sd_beta), rnorm(p)) + post_mean_beta)
+    w[, i] <- (y - X %*% beta[i, ]) / tau2[i]                                         # :92
+    eps[, i] <- rnorm(N)                                                              # :93
+  }
+  res <- .Call(spw_r_spsample_run, .spw_type(cov.type), as.matrix(coords) + 0, as.numeric(phi), as.numeric(sig2),
+               as.numeric(tau2), w, eps)
+  z <- res[[1]]; bad <- res[[2]]; beta0 <- numeric(S); z.last <- NULL
+  for (i in seq_len(S)) {                                                             # "Bad Iteration" rule, :85-89 (one chunk)
+    if (bad[i] != 0) {
+      if (!silent) cat("Bad Iteration::", i, "\n")
+      z[i, ] <- if (i == 1) 0 else if (i == 2) z[1, ] else apply(z[1:(i - 1), , drop = FALSE], 2, median)
+    } else z.last <- z[i, ]
+    beta0[i] <- mean(z.last)                                                          # :99
+  }
+  list(z = z, beta0 = beta0, beta = as.vector(beta))                                  # :110-112
+}

@@ -60,10 +60,35 @@ SEXP spw_r_gradient_run(SEXP type, SEXP coords, SEXP grid, SEXP phi, SEXP sig2, 
   return ans;
 }
 
+/* spsample, N x N part  --  R/spsample_beta.R:50-100 (w = (y - X beta)/tau2 per sample and eps are n x S) */
+SEXP spw_r_spsample_run(SEXP type, SEXP coords, SEXP phi, SEXP sig2, SEXP tau2, SEXP w, SEXP eps) {
+  const int n = Rf_nrows(coords), S = Rf_length(phi);
+  SEXP ans = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP z = PROTECT(Rf_allocMatrix(REALSXP, S, n));
+  SEXP bad = PROTECT(Rf_allocVector(INTSXP, S));
+  int info[4];
+  spw_stop(spw_spsample_run(Rf_asInteger(type), n, REAL(coords), S, REAL(phi), REAL(sig2), REAL(tau2), REAL(w), REAL(eps),
+                            REAL(z), INTEGER(bad), info));
+  SET_VECTOR_ELT(ans, 0, z); SET_VECTOR_ELT(ans, 1, bad);
+  UNPROTECT(3);
+  return ans;
+}
+
+/* posterior surface analysis  --  README.md:123-177; draws is the S x g x 5 array of grad.s*.mcmc */
+SEXP spw_r_surface_analysis(SEXP draws, SEXP S, SEXP g, SEXP nbatch) {
+  const int s = Rf_asInteger(S), gg = Rf_asInteger(g);
+  SEXP summ = PROTECT(Rf_alloc3DArray(REALSXP, gg, 3, 5));
+  spw_stop(spw_surface_analysis(s, gg, REAL(draws), Rf_asInteger(nbatch), 0.95, REAL(summ), NULL));
+  UNPROTECT(1);
+  return summ;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"spw_r_cov_delta", (DL_FUNC)&spw_r_cov_delta, 4},
   {"spw_r_hlm_run", (DL_FUNC)&spw_r_hlm_run, 10},
   {"spw_r_gradient_run", (DL_FUNC)&spw_r_gradient_run, 10},
+  {"spw_r_spsample_run", (DL_FUNC)&spw_r_spsample_run, 7},
+  {"spw_r_surface_analysis", (DL_FUNC)&spw_r_surface_analysis, 4},
   {NULL, NULL, 0}
 };
 

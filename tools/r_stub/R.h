@@ -5,9 +5,11 @@
 #include <stddef.h>
 typedef struct SEXPREC* SEXP;
 typedef ptrdiff_t R_xlen_t;
+#define INTSXP 13
 #define REALSXP 14
 #define VECSXP 19
 double* REAL(SEXP);
+int* INTEGER(SEXP);
 int Rf_asInteger(SEXP);
 double Rf_asReal(SEXP);
 int Rf_asLogical(SEXP);
