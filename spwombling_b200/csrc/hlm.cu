@@ -130,41 +130,57 @@ __device__ void hlm_init_state(HlmState& s) {
 __global__ void hlm_init_state_kernel(HlmState* S) { hlm_init_state(*S); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small systems (n <= HLM_SMALL_MAX): the whole chain in ONE persistent CTA with the matrix in REGISTERS.
-// Thread (ta, tb) of a 16 x 16 grid owns the elements (i, k) = (ta + 16 r, tb + 16 c), c <= r, of the augmented
-// lower matrix [Sigma'; y^T]; each proposal re-assembles them from the coordinates (no shared-memory matrix at all)
-// and factors in LDL^T form, right-looking: per column the owners publish the raw column to shared memory, ONE
-// barrier, every thread updates its registers.  Column j stays "raw" (L[i][j] = raw[i][j] / sqrt(d_j)), so
-// y' Sigma^-1 y = sum_j raw[n][j]^2 / d_j and sum(log(diag(chol))) = 1/2 sum_j log d_j need no square roots.
-// Launch-bound configurations (README N = 100, meuse N = 155) avoid ~27 kernel launches per iteration this way.
+// Small systems (n <= HLM_SMALL_MAX): the whole chain in ONE persistent CTA, the matrix resident in shared memory.
+// The augmented lower matrix [Sigma'; y^T] is stored as packed 4 x 4 tiles (tile (ti, tk), tk <= ti, at tile index
+// ti (ti + 1) / 2 + tk, 18 doubles apart so that 128-bit accesses of neighbouring threads hit different banks); the
+// columns are padded to a multiple of 4 with identity and the row y^T starts a tile row of its own, so it is never a
+// pivot row.  Each proposal re-assembles the tiles from the coordinates and factors them right-looking, four pivots
+// at a time with two barriers per tile column:
+//   (A) one thread per tile below the pivot tile factors the 4 x 4 pivot tile (redundantly, reciprocal square roots)
+//       and solves its own tile X = C Ld^-T in place -- these are final entries of L;
+//   (B) every tile to the right takes its rank-4 update X_i X_k^T.
+// y' Sigma^-1 y is the squared norm of the y tile row, sum(log(diag(chol))) the sum of the logs of the pivots.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int HLM_SMALL_THREADS = 256;
+constexpr int HLM_SMALL_THREADS = 512;
+constexpr int HLM_TS = 18;                              // doubles between consecutive tiles
 
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+__device__ __forceinline__ void tile_load(const double* t, double (&a)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const double2 u = *reinterpret_cast<const double2*>(t + 4 * r);
+    const double2 v = *reinterpret_cast<const double2*>(t + 4 * r + 2);
+    a[r][0] = u.x; a[r][1] = u.y; a[r][2] = v.x; a[r][3] = v.y;
+  }
+}
+__device__ __forceinline__ void tile_store(double* t, const double (&a)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    *reinterpret_cast<double2*>(t + 4 * r) = make_double2(a[r][0], a[r][1]);
+    *reinterpret_cast<double2*>(t + 4 * r + 2) = make_double2(a[r][2], a[r][3]);
+  }
 }
 
-template <int TYPE, int NT>
+template <int TYPE>
 __global__ void __launch_bounds__(HLM_SMALL_THREADS, 1)
 hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict__ cy, const double* __restrict__ y,
                  HlmState* Sg, HlmConst c, const double* __restrict__ norm, const double* __restrict__ unif, HlmOut o,
                  int* __restrict__ status) {
-  __shared__ double sx[16 * NT], sy[16 * NT], syv[16 * NT];
-  __shared__ double colbuf[2][16 * NT];
-  __shared__ double dvec[16 * NT], wvec[16 * NT];      // pivots d_j and raw y-row entries, reduced after the sweep
-  __shared__ double red[2][8];
+  extern __shared__ __align__(16) double hs[];
+  const int NC = (n + 3) / 4;                           // tile columns (pivot groups)
+  const int NR = NC + 1;                                // tile rows: NC matrix tile rows + the y tile row
+  const int ntiles = NC * (NC + 1) / 2 + NC;            // lower tiles of the matrix + the y tile row
+  double* T = hs;                                       // ntiles * HLM_TS
+  double* sx = T + (size_t)ntiles * HLM_TS;
+  double* sy = sx + 4 * NC;
+  double* syv = sy + 4 * NC;
+  double* diagv = syv + 4 * NC;                         // pivots l_jj
+  double* red = diagv + 4 * NC;                         // 2 x 16 partial sums
+  unsigned short* tl = reinterpret_cast<unsigned short*>(red + 32);   // tile list sorted by tile column: (ti << 8) | tk
+  int* tstart = reinterpret_cast<int*>(tl + ((ntiles + 3) & ~3));     // first list entry of each tile column (+ end)
   __shared__ HlmState s;
   __shared__ int bad;
   const int tid = threadIdx.x;
-  const int ta = tid >> 4, tb = tid & 15;
-  for (int i = tid; i < 16 * NT; i += HLM_SMALL_THREADS) {
+  for (int i = tid; i < 4 * NC; i += HLM_SMALL_THREADS) {
     sx[i] = (i < n) ? cx[i] : 0.0;
     sy[i] = (i < n) ? cy[i] : 0.0;
     syv[i] = (i < n) ? y[i] : 0.0;
@@ -172,88 +188,129 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
   if (tid == 0) {
     hlm_init_state(s);
     bad = 0;
+    int e = 0;
+    for (int tk = 0; tk < NC; ++tk) {
+      tstart[tk] = e;
+      for (int ti = tk; ti < NR; ++ti) tl[e++] = (unsigned short)((ti << 8) | tk);
+    }
+    tstart[NC] = e;
   }
   __syncthreads();
-  double a[NT][NT];                                    // a[r][cc] for cc <= r (the rest is never touched)
-  const int total_steps = 1 + 3 * c.niter;             // initial factorisation + 3 proposals per iteration
+  const int total_steps = 1 + 3 * c.niter;              // initial factorisation + 3 proposals per iteration
   for (int step = 0; step < total_steps; ++step) {
     const int p = (step == 0) ? -1 : (step - 1) % 3;
     if (tid == 0) hlm_propose(s, c, p, norm);
     __syncthreads();
     const double ph = s.prop[2], s2 = s.prop[0], t2 = s.prop[1];
-    // ---- assemble this thread's elements of Sigma' = sig2 R(phi) + tau2 I and of the row y^T ----
+    // ---- assemble all tiles ----
+    for (int e = tid; e < ntiles; e += HLM_SMALL_THREADS) {
+      const int ti = tl[e] >> 8, tk = tl[e] & 255;
+      double a[4][4];
 #pragma unroll
-    for (int r = 0; r < NT; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int cc = 0; cc <= r; ++cc) {
-        const int i = ta + 16 * r, k = tb + 16 * cc;
-        double v = 0.0;
-        if (k < n && i <= n && i >= k) {
-          if (i == n) {
-            v = syv[k];
+        for (int cc = 0; cc < 4; ++cc) {
+          const int i = 4 * ti + r, k = 4 * tk + cc;
+          double v = 0.0;
+          if (ti == NC) {                               // the y tile row: y^T in its first row
+            if (r == 0 && k < n) v = syv[k];
+          } else if (i >= n || k >= n) {
+            v = (i == k) ? 1.0 : 0.0;                   // identity padding
           } else if (i == k) {
             v = s2 + t2;
-          } else {
+          } else if (k < i) {
             const double dx = sx[i] - sx[k], dy = sy[i] - sy[k];
             const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
             v = s2 * cov_rho<TYPE>(ph, d);
           }
+          a[r][cc] = v;
         }
-        a[r][cc] = v;
-      }
-    // ---- right-looking LDL^T, one barrier per column; thread 0 accumulates log d_j and raw[n][j]^2 / d_j ----
-    for (int j = 0; j < n; ++j) {
-      const int jr = j >> 4, jb = j & 15;
-      double* cb = colbuf[j & 1];
-      if (tb == jb) {                                  // owners of column j publish it (rows i = ta + 16 r >= j)
-#pragma unroll
-        for (int r = 0; r < NT; ++r)
-#pragma unroll
-          for (int cc = 0; cc <= r; ++cc)
-            if (cc == jr) cb[ta + 16 * r] = a[r][cc];
-      }
-      __syncthreads();
-      const double dj = cb[j];
-      const double inv = fast_rcp(dj);
-      if (tid == HLM_SMALL_THREADS - 1) {              // bookkeeping off the critical path (last warp owns few elements)
-        if (!(dj > 0.0) && bad == 0) bad = j + 1;
-        dvec[j] = dj;
-        wvec[j] = cb[n];
-      }
-      double ci[NT], ck[NT];
-#pragma unroll
-      for (int r = 0; r < NT; ++r) {
-        ci[r] = cb[ta + 16 * r];
-        ck[r] = cb[tb + 16 * r] * inv;
-      }
-#pragma unroll
-      for (int r = 0; r < NT; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc) {
-          const int i = ta + 16 * r, k = tb + 16 * cc;
-          if (k > j && i >= k) a[r][cc] = fma(-ci[r], ck[cc], a[r][cc]);   // rows beyond n / columns >= n hold zeros
-        }
+      tile_store(T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS, a);
     }
     __syncthreads();
+    // ---- factorisation: NC tile columns ----
+    for (int jb = 0; jb < NC; ++jb) {
+      // (A) threads 0 .. NR - jb - 1: thread t owns tile (jb + t, jb); t = 0 is the pivot tile itself
+      if (tid < NR - jb) {
+        const int ti = jb + tid;
+        double D[4][4];
+        tile_load(T + (size_t)(jb * (jb + 1) / 2 + jb) * HLM_TS, D);
+        const double q0 = D[0][0], rs0 = fast_rsqrt(q0);
+        const double l10 = D[1][0] * rs0, l20 = D[2][0] * rs0, l30 = D[3][0] * rs0;
+        const double q1 = fma(-l10, l10, D[1][1]), rs1 = fast_rsqrt(q1);
+        const double l21 = fma(-l20, l10, D[2][1]) * rs1, l31 = fma(-l30, l10, D[3][1]) * rs1;
+        const double q2 = fma(-l21, l21, fma(-l20, l20, D[2][2])), rs2 = fast_rsqrt(q2);
+        const double l32 = fma(-l31, l21, fma(-l30, l20, D[3][2])) * rs2;
+        const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[3][3]))), rs3 = fast_rsqrt(q3);
+        if (tid == 0) {
+          int first_bad = 0;
+          if (!(q3 > 0.0)) first_bad = 4;
+          if (!(q2 > 0.0)) first_bad = 3;
+          if (!(q1 > 0.0)) first_bad = 2;
+          if (!(q0 > 0.0)) first_bad = 1;
+          if (first_bad && bad == 0) bad = 4 * jb + first_bad;
+          diagv[4 * jb + 0] = q0 * rs0;
+          diagv[4 * jb + 1] = q1 * rs1;
+          diagv[4 * jb + 2] = q2 * rs2;
+          diagv[4 * jb + 3] = q3 * rs3;
+        } else {
+          double* tp = T + (size_t)(ti * (ti + 1) / 2 + jb) * HLM_TS;
+          double C[4][4];
+          tile_load(tp, C);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double x0 = C[r][0] * rs0;
+            const double x1 = fma(-x0, l10, C[r][1]) * rs1;
+            const double x2 = fma(-x1, l21, fma(-x0, l20, C[r][2])) * rs2;
+            const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, C[r][3]))) * rs3;
+            C[r][0] = x0; C[r][1] = x1; C[r][2] = x2; C[r][3] = x3;
+          }
+          tile_store(tp, C);
+        }
+      }
+      __syncthreads();
+      // (B) rank-4 update of every tile (ti, tk) with tk > jb
+      for (int e = tstart[jb + 1] + tid; e < ntiles; e += HLM_SMALL_THREADS) {
+        const int ti = tl[e] >> 8, tk = tl[e] & 255;
+        double xi[4][4], xk[4][4], a[4][4];
+        tile_load(T + (size_t)(ti * (ti + 1) / 2 + jb) * HLM_TS, xi);
+        tile_load(T + (size_t)(tk * (tk + 1) / 2 + jb) * HLM_TS, xk);
+        double* tp = T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS;
+        tile_load(tp, a);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            double acc = a[r][cc];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = fma(-xi[r][k], xk[cc][k], acc);
+            a[r][cc] = acc;
+          }
+        tile_store(tp, a);
+      }
+      __syncthreads();
+    }
+    // ---- sum_j log l_jj and |L[y][.]|^2 ----
     double sl = 0.0, sq = 0.0;
     for (int j = tid; j < n; j += HLM_SMALL_THREADS) {
-      sl += log(dvec[j]);
-      sq += wvec[j] * wvec[j] / dvec[j];
+      sl += log(diagv[j]);
+      const double w = T[(size_t)(NC * (NC + 1) / 2 + (j >> 2)) * HLM_TS + (j & 3)];   // row 0 of the y tile row
+      sq = fma(w, w, sq);
     }
     sl = warp_sum(sl);
     sq = warp_sum(sq);
     if ((tid & 31) == 0) {
-      red[0][tid >> 5] = sl;
-      red[1][tid >> 5] = sq;
+      red[tid >> 5] = sl;
+      red[16 + (tid >> 5)] = sq;
     }
     __syncthreads();
     if (tid == 0) {
       double al = 0.0, aq = 0.0;
       for (int w = 0; w < HLM_SMALL_THREADS / 32; ++w) {
-        al += red[0][w];
-        aq += red[1][w];
+        al += red[w];
+        aq += red[16 + w];
       }
-      s.logdet_p = 0.5 * al;
+      s.logdet_p = al;
       s.quad_p = aq;
       hlm_accept(s, c, p, unif, o);
     }
@@ -265,13 +322,18 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
   }
 }
 
+static size_t hlm_small_smem(int n) {
+  const size_t NC = (n + 3) / 4, ntiles = NC * (NC + 1) / 2 + NC;
+  return (ntiles * HLM_TS + 4 * 4 * NC + 32) * sizeof(double) + ((ntiles + 3) & ~(size_t)3) * sizeof(unsigned short) +
+         (NC + 2) * sizeof(int) + 64;
+}
+
 template <int TYPE>
 static int hlm_small_launch(int n, const double* cx, const double* cy, const double* y, HlmState* S, const HlmConst& c,
                             const double* norm, const double* unif, const HlmOut& ho, int* status, cudaStream_t st) {
-  const int nt = (n + 1 + 15) / 16;
-  if (nt <= 4) hlm_small_kernel<TYPE, 4><<<1, HLM_SMALL_THREADS, 0, st>>>(n, cx, cy, y, S, c, norm, unif, ho, status);
-  else if (nt <= 7) hlm_small_kernel<TYPE, 7><<<1, HLM_SMALL_THREADS, 0, st>>>(n, cx, cy, y, S, c, norm, unif, ho, status);
-  else hlm_small_kernel<TYPE, 11><<<1, HLM_SMALL_THREADS, 0, st>>>(n, cx, cy, y, S, c, norm, unif, ho, status);
+  const size_t smem = hlm_small_smem(n);
+  SPW_CUDA(cudaFuncSetAttribute(hlm_small_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hlm_small_kernel<TYPE><<<1, HLM_SMALL_THREADS, smem, st>>>(n, cx, cy, y, S, c, norm, unif, ho, status);
   SPW_LAUNCHED();
   return SPW_OK;
 }
@@ -288,10 +350,11 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
   const HlmOut ho{out_sig2, out_tau2, out_phi, out_trgt, out_accept, out_tuning, nrep};
   SPW_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(int), st));
   {
-    // opt-in: measured on B200 the single-CTA chain is instruction-issue bound (~70 us per factorisation at n = 100)
-    // and no faster than the blocked multi-kernel path replayed as a CUDA graph, so it is not the default
+    // default for n <= HLM_SMALL_DEFAULT_MAX, where the single-CTA chain beats the blocked multi-kernel path replayed as a
+    // CUDA graph (10.7k vs 5.1k it/s at n = 100, 5.0k vs 3.7k at n = 155, equal at n = 200); SPW_HLM_SMALL=0 / 1 forces
+    // the choice (1: up to HLM_SMALL_MAX)
     const char* env_small = getenv("SPW_HLM_SMALL");
-    const bool allow_small = (env_small && env_small[0] == '1');
+    const bool allow_small = env_small ? (env_small[0] == '1') : (n <= HLM_SMALL_DEFAULT_MAX);
     if (allow_small && n <= HLM_SMALL_MAX) {
       switch (type) {
         case 0: SPW_TRY(hlm_small_launch<0>(n, cx, cy, y_dev, S, c, norm_dev, unif_dev, ho, ws.status, st)); break;

@@ -268,7 +268,8 @@ def test_hlm_chain_vs_oracle(spw, n, cov_type, niter, report):
 
 
 def test_hlm_defaults_and_graph_equivalence(spw, monkeypatch):
-    """Graph replay and eager launches produce the same chain (bit-identical)."""
+    """Graph replay and eager launches of the blocked path produce the same chain (bit-identical)."""
+    monkeypatch.setenv("SPW_HLM_SMALL", "0")
     rng = np.random.default_rng(2)
     coords = rng.random((64, 2))
     y = rng.standard_normal(64)
@@ -375,8 +376,9 @@ def test_hlm_opt_in_paths(spw, monkeypatch):
     y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
     kw = dict(y=y, coords=coords, niter=niter, nburn=10, report=10, cov_type="matern2",
               norm=rng.standard_normal(3 * niter), unif=rng.random(3 * niter), trgtFn_compute=True, verbose=False)
+    monkeypatch.setenv("SPW_HLM_SMALL", "0")          # blocked multi-kernel path (CUDA graph per iteration)
     base = spw.hlmBayes_sp(**kw)
-    monkeypatch.setenv("SPW_HLM_SMALL", "1")          # single-CTA register-resident chain (n <= 175)
+    monkeypatch.setenv("SPW_HLM_SMALL", "1")          # single-CTA shared-memory chain (default for n <= 176)
     small = spw.hlmBayes_sp(**kw)
     monkeypatch.delenv("SPW_HLM_SMALL")
     for key in ("sig2", "tau2", "phi", "trgt_fn"):
