@@ -135,10 +135,9 @@ __global__ void hlm_init_state_kernel(HlmState* S) { hlm_init_state(*S); }
 // ti (ti + 1) / 2 + tk, 18 doubles apart so that 128-bit accesses of neighbouring threads hit different banks); the
 // columns are padded to a multiple of 4 with identity and the row y^T starts a tile row of its own, so it is never a
 // pivot row.  Each proposal re-assembles the tiles from the coordinates and factors them right-looking, four pivots
-// at a time with two barriers per tile column:
-//   (A) one thread per tile below the pivot tile factors the 4 x 4 pivot tile (redundantly, reciprocal square roots)
-//       and solves its own tile X = C Ld^-T in place -- these are final entries of L;
-//   (B) every tile to the right takes its rank-4 update X_i X_k^T.
+// at a time with one barrier per tile column: one thread per tile of the column factors the 4 x 4 pivot tile
+// (redundantly, reciprocal square roots) and solves its own tile X = C Ld^-T in place -- final entries of L -- while
+// the remaining threads give every tile further right its rank-4 update X_i X_k^T of the previous column.
 // y' Sigma^-1 y is the squared norm of the y tile row, sum(log(diag(chol))) the sum of the logs of the pivots.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int HLM_SMALL_THREADS = 512;
@@ -228,13 +227,27 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
       tile_store(T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS, a);
     }
     __syncthreads();
-    // ---- factorisation: NC tile columns ----
+    // ---- factorisation: NC tile columns, ONE barrier each.  In step jb the "owner" threads (one per tile of tile
+    //      column jb) first apply the pending update of column jb - 1 to their own tile and to a private copy of the
+    //      pivot tile, then factor / solve (their tiles are final after this step); meanwhile the worker threads apply
+    //      the update of column jb - 1 to all tiles right of column jb. ----
     for (int jb = 0; jb < NC; ++jb) {
-      // (A) threads 0 .. NR - jb - 1: thread t owns tile (jb + t, jb); t = 0 is the pivot tile itself
       if (tid < NR - jb) {
         const int ti = jb + tid;
-        double D[4][4];
+        double D[4][4], xk[4][4];
         tile_load(T + (size_t)(jb * (jb + 1) / 2 + jb) * HLM_TS, D);
+        if (jb > 0) {
+          tile_load(T + (size_t)(jb * (jb + 1) / 2 + jb - 1) * HLM_TS, xk);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc <= r; ++cc) {
+              double acc = D[r][cc];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc = fma(-xk[r][k], xk[cc][k], acc);
+              D[r][cc] = acc;
+            }
+        }
         const double q0 = D[0][0], rs0 = fast_rsqrt(q0);
         const double l10 = D[1][0] * rs0, l20 = D[2][0] * rs0, l30 = D[3][0] * rs0;
         const double q1 = fma(-l10, l10, D[1][1]), rs1 = fast_rsqrt(q1);
@@ -257,6 +270,19 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
           double* tp = T + (size_t)(ti * (ti + 1) / 2 + jb) * HLM_TS;
           double C[4][4];
           tile_load(tp, C);
+          if (jb > 0) {
+            double xi[4][4];
+            tile_load(T + (size_t)(ti * (ti + 1) / 2 + jb - 1) * HLM_TS, xi);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                double acc = C[r][cc];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma(-xi[r][k], xk[cc][k], acc);
+                C[r][cc] = acc;
+              }
+          }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const double x0 = C[r][0] * rs0;
@@ -267,26 +293,27 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
           }
           tile_store(tp, C);
         }
-      }
-      __syncthreads();
-      // (B) rank-4 update of every tile (ti, tk) with tk > jb
-      for (int e = tstart[jb + 1] + tid; e < ntiles; e += HLM_SMALL_THREADS) {
-        const int ti = tl[e] >> 8, tk = tl[e] & 255;
-        double xi[4][4], xk[4][4], a[4][4];
-        tile_load(T + (size_t)(ti * (ti + 1) / 2 + jb) * HLM_TS, xi);
-        tile_load(T + (size_t)(tk * (tk + 1) / 2 + jb) * HLM_TS, xk);
-        double* tp = T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS;
-        tile_load(tp, a);
+      } else if (tid >= 64 && jb > 0) {
+        // workers: rank-4 update with column jb - 1 of every tile (ti, tk), tk > jb
+        const int jp = jb - 1;
+        for (int e = tstart[jb + 1] + (tid - 64); e < ntiles; e += HLM_SMALL_THREADS - 64) {
+          const int ti = tl[e] >> 8, tk = tl[e] & 255;
+          double xi[4][4], xk[4][4], a[4][4];
+          tile_load(T + (size_t)(ti * (ti + 1) / 2 + jp) * HLM_TS, xi);
+          tile_load(T + (size_t)(tk * (tk + 1) / 2 + jp) * HLM_TS, xk);
+          double* tp = T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS;
+          tile_load(tp, a);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            double acc = a[r][cc];
+            for (int cc = 0; cc < 4; ++cc) {
+              double acc = a[r][cc];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc = fma(-xi[r][k], xk[cc][k], acc);
-            a[r][cc] = acc;
-          }
-        tile_store(tp, a);
+              for (int k = 0; k < 4; ++k) acc = fma(-xi[r][k], xk[cc][k], acc);
+              a[r][cc] = acc;
+            }
+          tile_store(tp, a);
+        }
       }
       __syncthreads();
     }
@@ -351,8 +378,8 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
   SPW_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(int), st));
   {
     // default for n <= HLM_SMALL_DEFAULT_MAX, where the single-CTA chain beats the blocked multi-kernel path replayed as a
-    // CUDA graph (10.7k vs 5.1k it/s at n = 100, 5.0k vs 3.7k at n = 155, equal at n = 200); SPW_HLM_SMALL=0 / 1 forces
-    // the choice (1: up to HLM_SMALL_MAX)
+    // CUDA graph (12.0k vs 5.1k it/s at n = 100, 5.6k vs 3.7k at n = 155, 3.0k vs 2.8k at n = 200); SPW_HLM_SMALL=0 / 1
+    // forces the choice (1: up to HLM_SMALL_MAX)
     const char* env_small = getenv("SPW_HLM_SMALL");
     const bool allow_small = env_small ? (env_small[0] == '1') : (n <= HLM_SMALL_DEFAULT_MAX);
     if (allow_small && n <= HLM_SMALL_MAX) {

@@ -18,7 +18,7 @@ struct HlmWorkspace {
 };
 
 size_t hlm_state_bytes();
-constexpr int HLM_SMALL_DEFAULT_MAX = 176;   // the single-CTA chain is the default up to this order
+constexpr int HLM_SMALL_DEFAULT_MAX = 200;   // the single-CTA chain is the default up to this order
 constexpr int HLM_SMALL_MAX = 200;   // largest n handled by the single-CTA chain (packed 4 x 4 tiles in shared memory)
 
 // All pointers are device pointers except info_host.  Outputs as documented for spw_hlm_run.

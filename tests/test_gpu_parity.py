@@ -378,7 +378,7 @@ def test_hlm_opt_in_paths(spw, monkeypatch):
               norm=rng.standard_normal(3 * niter), unif=rng.random(3 * niter), trgtFn_compute=True, verbose=False)
     monkeypatch.setenv("SPW_HLM_SMALL", "0")          # blocked multi-kernel path (CUDA graph per iteration)
     base = spw.hlmBayes_sp(**kw)
-    monkeypatch.setenv("SPW_HLM_SMALL", "1")          # single-CTA shared-memory chain (default for n <= 176)
+    monkeypatch.setenv("SPW_HLM_SMALL", "1")          # single-CTA shared-memory chain (default for n <= 200)
     small = spw.hlmBayes_sp(**kw)
     monkeypatch.delenv("SPW_HLM_SMALL")
     for key in ("sig2", "tau2", "phi", "trgt_fn"):
