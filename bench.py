@@ -332,7 +332,7 @@ def bench_hlm(spw, args):
         out["n%d" % n] = {"iters_per_s": its, "niter": niter,
                           "cholesky_tflops": its * 3 * n ** 3 / 3.0 / 1e12,
                           "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H included); 3 Cholesky "
-                                  "factorisations of order n+1 per iteration (n <= 176: single persistent CTA)"}
+                                  "factorisations of order n+1 per iteration (n <= 200: single persistent CTA)"}
     if not args.no_cpu:
         from oracle import baseline
         n = 5000
