@@ -58,8 +58,8 @@ int spw_last_gather_used_nccl(void);
 int spw_profile_enable(int on);
 int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset);
 
-/* diagnostic: first call enables cycle counters in the diagonal-block kernel, later calls read them */
-int spw_debug_diag_timing(long long* out5);
+/* diagnostic: first call enables cycle counters in the diagonal-block kernel, later calls read 16 of them */
+int spw_debug_diag_timing(long long* out16);
 
 /* covariance kernels ----------------------------------------------------------------------------
  * spw_cov: as.matrix(dist(coords)) fused with cov_gaussian / cov_matern1 / cov_matern2

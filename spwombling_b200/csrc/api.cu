@@ -544,15 +544,16 @@ int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset
   return SPW_OK;
 }
 
-// diagnostic: cycle counters of the last diagonal-block kernel (load, factor, write-back, inverse, publish)
-int spw_debug_diag_timing(long long* out5) {
+// diagnostic: cycle counters of the last diagonal-block kernel: [0] load, [1] end of the factor + inverse sweep,
+// [4] end of kernel
+int spw_debug_diag_timing(long long* out16) {
   if (!g_diag_dbg) {
-    SPW_CUDA(cudaMalloc(&g_diag_dbg, 8 * sizeof(long long)));
-    SPW_CUDA(cudaMemset(g_diag_dbg, 0, 8 * sizeof(long long)));
+    SPW_CUDA(cudaMalloc(&g_diag_dbg, 16 * sizeof(long long)));
+    SPW_CUDA(cudaMemset(g_diag_dbg, 0, 16 * sizeof(long long)));
     return SPW_OK;
   }
   SPW_CUDA(cudaDeviceSynchronize());
-  SPW_CUDA(cudaMemcpy(out5, g_diag_dbg, 5 * sizeof(long long), cudaMemcpyDeviceToHost));
+  SPW_CUDA(cudaMemcpy(out16, g_diag_dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return SPW_OK;
 }
 

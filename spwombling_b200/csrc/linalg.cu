@@ -166,225 +166,335 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Diagonal block: factor the bs x bs lower block (bs <= 64), write it back, invert the factor, publish the inverse.
-// 256 threads.  Cholesky: right-looking with the block held in registers (thread (ti, tk) owns the 4 x 4 tile at
-// rows 4ti.., cols 4tk..); the 64 pivots are taken four at a time: the owners of tile column jb publish their raw
-// tiles, ONE barrier, and every thread redundantly factors the 4 x 4 pivot tile, solves its own two 4 x 4
-// triangular systems and applies the rank-4 update to its tile (one barrier per 4 columns instead of per column).
-// Inverse: 16 x 16 diagonal blocks by forward substitution, then X21 = -X22 (L21 X11) for the 32- and 64-blocks as
-// small dense products (zeros above the diagonals make every loop a fixed-length, fully unrolled one).
+// Diagonal block: factor the bs x bs lower block (bs <= 64) and invert the factor in the same sweep.
+// The sweep is latency-bound on ONE warp's dependent FP64 chain (cycle probes: a lone warp issues a DFMA every
+// 2.1 cycles, a dependent one every 8.3, the reciprocal square root takes 49), so the design keeps that warp's
+// instruction stream minimal and divergence-free and gives every other job to other warps.  384 threads in 12 warps:
+//   * warp 0, lanes s..15: the owners of tile column s (4 pivots).  They read the column as published one step
+//     earlier, apply the pending rank-4 update of column s-1 to the pivot tile and to their own tile, factor the
+//     pivot tile (redundantly, reciprocal square roots) and solve X = C Ld^-T: final tiles of L.
+//   * 136 threads (warps 1,2,3,5,6) each keep one 4 x 4 tile (ti, tk), ti >= tk, of the trailing block in registers, apply the
+//     update of column s-1 and publish column s+1 for the next step.
+//   * 120 threads (warps 7,9,10,11) each build one off-diagonal 4 x 4 tile (i, c) of X = L^-1,
+//     X[i][c] = -Xd_i sum_{k=c}^{i-1} L[i][k] X[k][c], one tile product per step as its operands become final.
+//   * one thread of warp 4 turns the pivot-tile numbers of the previous step into the diagonal tiles of L and X and checks
+//     the pivots.
+// One barrier per step, 18 steps; final tiles live in shared memory (packed 4 x 4, 18-double stride: conflict-free
+// 128-bit accesses) and all global writes (factor, 64 x 64 inverse block for the panel product, mirrored copy in
+// the triangular-inverse buffer) happen once at the end, by all threads.
 // ---------------------------------------------------------------------------------------------------
-constexpr int DIAG_THREADS = 256;
-long long* g_diag_dbg = nullptr;   // optional device buffer of 8 cycle counters (spw_debug_diag_timing)
+constexpr int DIAG_NT = NB / 4;                              // 16 tile rows
+constexpr int DIAG_LOW = DIAG_NT * (DIAG_NT + 1) / 2;        // 136 lower tiles
+constexpr int DIAG_OFF = DIAG_NT * (DIAG_NT - 1) / 2;        // 120 off-diagonal tiles
+constexpr int DIAG_THREADS = 384;                            // 12 warps; warps 4 and 8 only take part in the barriers
+constexpr int DIAG_HELPER = 4 * 32;                          // a lane of an otherwise idle warp
+constexpr int DIAG_TS = 18;                                  // tile stride in doubles
+long long* g_diag_dbg = nullptr;   // optional device buffer of 16 cycle counters (spw_debug_diag_timing)
 
-template <int S>
-__device__ __forceinline__ void diag_inverse_level(double (*Ls)[NB + 1], double (*Xs)[NB + 1], double (*Ts)[33], int tid) {
-  // pairs (b1 = 2 S p, b2 = b1 + S), p < NB / (2 S); each thread owns a 1 x 2 (S <= 16) or 2 x 2 (S = 32) block of
-  // the S x S outputs of its pair; threads beyond the work only take part in the barriers
-  constexpr int MR = (S == 32) ? 2 : 1;
-  constexpr int TPP = (S / MR) * (S / 2);                 // threads per pair
-  constexpr int NEED = TPP * (NB / (2 * S));              // 64, 128, 256, 256 for S = 4, 8, 16, 32
-  const bool work = tid < NEED;
-  const int p = tid / TPP, e = tid % TPP;
-  const int m0 = (e / (S / 2)) * MR, n0 = (e % (S / 2)) * 2;
-  const int b1 = 2 * S * p, b2 = b1 + S;
-  double acc[MR][2];
+__device__ __forceinline__ int diag_tile(int i, int k) { return DIAG_NT * k - (k * (k - 1)) / 2 + (i - k); }
+
+__device__ __forceinline__ void tile_load(const double* __restrict__ p, double (&t)[4][4]) {
 #pragma unroll
-  for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.0;
-  if (work) {
+  for (int r = 0; r < 4; ++r) {
+    const double2 u0 = *reinterpret_cast<const double2*>(p + 4 * r);
+    const double2 u1 = *reinterpret_cast<const double2*>(p + 4 * r + 2);
+    t[r][0] = u0.x; t[r][1] = u0.y; t[r][2] = u1.x; t[r][3] = u1.y;
+  }
+}
+
+__device__ __forceinline__ void tile_store(double* __restrict__ p, const double (&t)[4][4]) {
 #pragma unroll
-    for (int k = 0; k < S; ++k) {              // T = L21 X11   (X11 lower triangular: zeros supply the k >= n bound)
-      const double x0 = Xs[b1 + k][b1 + n0], x1 = Xs[b1 + k][b1 + n0 + 1];
+  for (int r = 0; r < 4; ++r) {
+    *reinterpret_cast<double2*>(p + 4 * r) = make_double2(t[r][0], t[r][1]);
+    *reinterpret_cast<double2*>(p + 4 * r + 2) = make_double2(t[r][2], t[r][3]);
+  }
+}
+
+// c -= a b^T
+__device__ __forceinline__ void tile_sub_abt(double (&c)[4][4], const double (&a)[4][4], const double (&b)[4][4]) {
 #pragma unroll
-      for (int i = 0; i < MR; ++i) {
-        const double l = Ls[b2 + m0 + i][b1 + k];
-        acc[i][0] = fma(l, x0, acc[i][0]);
-        acc[i][1] = fma(l, x1, acc[i][1]);
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double acc = c[r][q];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc = fma(-a[r][m], b[q][m], acc);
+      c[r][q] = acc;
+    }
+}
+
+// c += a b
+__device__ __forceinline__ void tile_add_ab(double (&c)[4][4], const double (&a)[4][4], const double (&b)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double acc = c[r][q];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc = fma(a[r][m], b[m][q], acc);
+      c[r][q] = acc;
+    }
+}
+
+// 4 x 4 tile at (row0, col0) of a row-major matrix; entries outside [0, bs) x [0, bs) are skipped (zero_outside = false)
+// or written as zero (true).  tr: write the transposed tile.
+__device__ __forceinline__ void tile_to_global(double* __restrict__ base, long long ld, int row0, int col0, int bs,
+                                               const double (&t)[4][4], bool tr, bool zero_outside) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = row0 + r;
+    if (!zero_outside && row >= bs) continue;
+    double* dst = base + (long long)row * ld + col0;
+#pragma unroll
+    for (int q = 0; q < 4; q += 2) {
+      double v0 = tr ? t[q][r] : t[r][q], v1 = tr ? t[q + 1][r] : t[r][q + 1];
+      const bool in0 = row < bs && col0 + q < bs, in1 = row < bs && col0 + q + 1 < bs;
+      if (zero_outside) {
+        *reinterpret_cast<double2*>(dst + q) = make_double2(in0 ? v0 : 0.0, in1 ? v1 : 0.0);
+      } else if (in1) {
+        *reinterpret_cast<double2*>(dst + q) = make_double2(v0, v1);
+      } else if (in0) {
+        dst[q] = v0;
       }
     }
-#pragma unroll
-    for (int i = 0; i < MR; ++i) {
-      Ts[p * S + m0 + i][n0] = acc[i][0];
-      Ts[p * S + m0 + i][n0 + 1] = acc[i][1];
-      acc[i][0] = acc[i][1] = 0.0;
-    }
   }
-  __syncthreads();
-  if (work) {
+}
+
+__device__ __forceinline__ void half_tile_load(const double* __restrict__ p, double (&t)[2][4]) {
 #pragma unroll
-    for (int k = 0; k < S; ++k) {              // X21 = -X22 T   (X22 lower triangular: zeros supply the k <= m bound)
-      const double t0 = Ts[p * S + k][n0], t1 = Ts[p * S + k][n0 + 1];
-#pragma unroll
-      for (int i = 0; i < MR; ++i) {
-        const double x = Xs[b2 + m0 + i][b2 + k];
-        acc[i][0] = fma(x, t0, acc[i][0]);
-        acc[i][1] = fma(x, t1, acc[i][1]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < MR; ++i) {
-      Xs[b2 + m0 + i][b1 + n0] = -acc[i][0];
-      Xs[b2 + m0 + i][b1 + n0 + 1] = -acc[i][1];
-    }
+  for (int r = 0; r < 2; ++r) {
+    const double2 u0 = *reinterpret_cast<const double2*>(p + 4 * r);
+    const double2 u1 = *reinterpret_cast<const double2*>(p + 4 * r + 2);
+    t[r][0] = u0.x; t[r][1] = u0.y; t[r][2] = u1.x; t[r][3] = u1.y;
   }
-  __syncthreads();
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nblk, MatView linv, int has_linv,
                    int* __restrict__ status, long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) double diag_smem[];
+  __shared__ __align__(16) double Lt[DIAG_LOW * DIAG_TS];          // final tiles of the factor
+  __shared__ __align__(16) double Xt[DIAG_LOW * DIAG_TS];          // final tiles of its inverse
+  __shared__ __align__(16) double Cn[2][DIAG_NT * DIAG_TS];        // tile column published for the next step
+  __shared__ __align__(16) double Dg[DIAG_NT][16];                 // pivot-tile numbers of each step
   long long t0 = 0;
   if (dbg && threadIdx.x == 0 && blockIdx.x == 0) t0 = clock64();
 #define DIAG_MARK(i) if (dbg && threadIdx.x == 0 && blockIdx.x == 0) dbg[i] = clock64() - t0;
-  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem);
-  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(diag_smem + NB * (NB + 1));
-  __shared__ __align__(16) double Tb[2][16][16];      // published raw pivot tile (double-buffered by column parity)
-  __shared__ __align__(16) double Xb[16][16];         // solved 4 x 4 blocks of the current tile column
-  __shared__ double Xd[16][16];                       // inverses of the 4 x 4 diagonal tiles
-  __shared__ double Ts[32][33];
-  __shared__ int bad;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int r0 = blk * NB, bs = min(NB, n - r0);
   double* Lp = L.p + (long long)b * L.stride + (long long)r0 * L.ld + r0;
-  if (tid == 0) bad = 0;
-  // ---- load: thread (ti, tk) reads its own 4 x 4 tile (identity-padded beyond bs) ----
-  const int ti = tid >> 4, tk = tid & 15;
-  const bool active = ti >= tk;
-  double a[4][4];
+  // roles by warp.  Warps are dealt to the four schedulers round-robin, so warp 0 (the critical path) keeps its
+  // scheduler's FP64 pipe to itself when warps 4 and 8 stay idle: update = warps 1,2,3,5,6; inverse = 7,9,10,11.
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool owner = warp == 0;          // lane = tile row + 16 * (row pair of the tile)
+  const int uidx = (warp < 4 ? warp - 1 : warp - 2) * 32 + lane;
+  const int iidx = (warp == 7 ? 0 : warp - 8) * 32 + lane;
+  const bool update = (warp == 1 || warp == 2 || warp == 3 || warp == 5 || warp == 6) && uidx < DIAG_LOW;
+  const bool inverse = (warp == 7 || warp >= 9) && iidx < DIAG_OFF;
+  int ti = 0, tk = 0;
+  if (update) {
+    int rem = uidx;
+    while (rem >= DIAG_NT - tk) { rem -= DIAG_NT - tk; ++tk; }
+    ti = tk + rem;
+  } else if (inverse) {
+    int rem = iidx;
+    while (rem >= DIAG_NT - 1 - tk) { rem -= DIAG_NT - 1 - tk; ++tk; }
+    ti = tk + 1 + rem;
+  } else if (owner) {
+    ti = tid & 15;
+  }
+  const int half = (tid >> 4) & 1;
+  double a[4][4];                        // update threads: the matrix tile; inverse threads: the running sum
 #pragma unroll
-  for (int ii = 0; ii < 4; ++ii)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int r = 4 * ti + ii, c = 4 * tk + kk;
-      double v = (r == c) ? 1.0 : 0.0;
-      if (active && r < bs && c <= r) v = Lp[(long long)r * L.ld + c];
-      a[ii][kk] = v;
-    }
+    for (int q = 0; q < 4; ++q) a[r][q] = 0.0;
+  if (update) {                          // identity-padded beyond bs; the strict upper part of diagonal tiles is unused
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = 4 * ti + r, col = 4 * tk + q;
+        double v = (row == col) ? 1.0 : 0.0;
+        if (row < bs && col <= row) v = Lp[(long long)row * L.ld + col];
+        a[r][q] = v;
+      }
+    if (tk == 0) tile_store(Cn[0] + ti * DIAG_TS, a);
+  }
+  __syncthreads();
   DIAG_MARK(0)
-  // ---- Cholesky, four pivots at a time, two barriers per tile column: (A) the owners of tile column jb factor the
-  //      4 x 4 pivot tile (redundantly, 16 threads) and solve their own 4 x 4 block X = C Ld^-T, which is final;
-  //      (B) every remaining tile takes its rank-4 update from the published X blocks ----
+  int base_prev = 0, base_cur = 0;       // diag_tile(i, s-1) = base_prev + i, diag_tile(i, s) = base_cur + i
 #pragma unroll 1
-  for (int jb = 0; jb < NB / 4; ++jb) {
-    double (*T)[16] = Tb[jb & 1];
-    if (tk == jb && ti == jb) {              // publish the raw pivot tile
+  for (int s = 0; s <= DIAG_NT + 1; base_prev = base_cur, base_cur += DIAG_NT - 1 - s, ++s) {
+    if (owner) {
+      // ---- owners of tile column s: two lanes per tile (two rows each), uniform instruction stream: this is the
+      //      critical path ----
+      const bool live = ti >= s && s < DIAG_NT;
+      double d[4][4], xk[4][4], c[2][4], xi[2][4];
+      if (live) {
+        tile_load(Cn[s & 1] + s * DIAG_TS, d);
+        half_tile_load(Cn[s & 1] + ti * DIAG_TS + 8 * half, c);
+        if (s > 0) {
+          tile_load(Lt + (base_prev + s) * DIAG_TS, xk);
+          half_tile_load(Lt + (base_prev + ti) * DIAG_TS + 8 * half, xi);
+        }
+      }
+      if (live) {
+        if (s > 0) {
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int kk = 0; kk < 4; kk += 2)
-          *reinterpret_cast<double2*>(&T[jb][ii * 4 + kk]) = make_double2(a[ii][kk], a[ii][kk + 1]);
-    }
-    __syncthreads();
-    if (tk == jb && active) {
-      const double* D = T[jb];
-      const double q0 = D[0], rs0 = fast_rsqrt(q0);
-      const double l10 = D[4] * rs0, l20 = D[8] * rs0, l30 = D[12] * rs0;
-      const double q1 = fma(-l10, l10, D[5]), rs1 = fast_rsqrt(q1);
-      const double l21 = fma(-l20, l10, D[9]) * rs1, l31 = fma(-l30, l10, D[13]) * rs1;
-      const double q2 = fma(-l21, l21, fma(-l20, l20, D[10])), rs2 = fast_rsqrt(q2);
-      const double l32 = fma(-l31, l21, fma(-l30, l20, D[14])) * rs2;
-      const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[15]))), rs3 = fast_rsqrt(q3);
-      if (ti == jb) {                        // the diagonal tile: final factor entries and the pivot check
-        int first_bad = 0;
-        if (!(q3 > 0.0)) first_bad = 4;
-        if (!(q2 > 0.0)) first_bad = 3;
-        if (!(q1 > 0.0)) first_bad = 2;
-        if (!(q0 > 0.0)) first_bad = 1;
-        if (first_bad && bad == 0) bad = r0 + 4 * jb + first_bad;
-        a[0][0] = q0 * rs0;
-        a[1][0] = l10; a[1][1] = q1 * rs1;
-        a[2][0] = l20; a[2][1] = l21; a[2][2] = q2 * rs2;
-        a[3][0] = l30; a[3][1] = l31; a[3][2] = l32; a[3][3] = q3 * rs3;
-        a[0][1] = a[0][2] = a[0][3] = a[1][2] = a[1][3] = a[2][3] = 0.0;
-        // 4 x 4 inverse of the diagonal tile: seeds the blocked inverse below
-        const double i00 = rs0, i11 = rs1, i22 = rs2, i33 = rs3;
+            for (int q = 0; q <= r; ++q) {
+              double acc = d[r][q];
+#pragma unroll
+              for (int m = 0; m < 4; ++m) acc = fma(-xk[r][m], xk[q][m], acc);
+              d[r][q] = acc;
+            }
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              double acc = c[r][q];
+#pragma unroll
+              for (int m = 0; m < 4; ++m) acc = fma(-xi[r][m], xk[q][m], acc);
+              c[r][q] = acc;
+            }
+        }
+        const double q0 = d[0][0], rs0 = fast_rsqrt(q0);
+        const double l10 = d[1][0] * rs0, l20 = d[2][0] * rs0, l30 = d[3][0] * rs0;
+        const double q1 = fma(-l10, l10, d[1][1]), rs1 = fast_rsqrt(q1);
+        const double l21 = fma(-l20, l10, d[2][1]) * rs1, l31 = fma(-l30, l10, d[3][1]) * rs1;
+        const double q2 = fma(-l21, l21, fma(-l20, l20, d[2][2])), rs2 = fast_rsqrt(q2);
+        const double l32 = fma(-l31, l21, fma(-l30, l20, d[3][2])) * rs2;
+        const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, d[3][3]))), rs3 = fast_rsqrt(q3);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {          // X = C Ld^-T (on the diagonal lanes this is idle work)
+          const double x0 = c[r][0] * rs0;
+          const double x1 = fma(-x0, l10, c[r][1]) * rs1;
+          const double x2 = fma(-x1, l21, fma(-x0, l20, c[r][2])) * rs2;
+          const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, c[r][3]))) * rs3;
+          c[r][0] = x0; c[r][1] = x1; c[r][2] = x2; c[r][3] = x3;
+        }
+        if (ti == s) {                         // the pivot-tile numbers, turned into tiles by the helper next step
+          if (half == 0) {
+            c[0][0] = l10; c[0][1] = l20; c[0][2] = l30; c[0][3] = l21;
+            c[1][0] = l31; c[1][1] = l32; c[1][2] = q0 * rs0; c[1][3] = q1 * rs1;
+          } else {
+            c[0][0] = q2 * rs2; c[0][1] = q3 * rs3; c[0][2] = rs0; c[0][3] = rs1;
+            c[1][0] = rs2; c[1][1] = rs3;
+          }
+        }
+        double* dst = (ti == s ? &Dg[s][0] : Lt + (base_cur + ti) * DIAG_TS) + 8 * half;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          *reinterpret_cast<double2*>(dst + 4 * r) = make_double2(c[r][0], c[r][1]);
+          *reinterpret_cast<double2*>(dst + 4 * r + 2) = make_double2(c[r][2], c[r][3]);
+        }
+      }
+    } else {
+      if (update) {
+        if (tk > s) {
+          // ---- the trailing block: update of column s-1; publish column s+1 for the next step ----
+          if (s > 0) {
+            double xi[4][4], xk[4][4];
+            tile_load(Lt + (base_prev + ti) * DIAG_TS, xi);
+            tile_load(Lt + (base_prev + tk) * DIAG_TS, xk);
+            tile_sub_abt(a, xi, xk);
+          }
+          if (tk == s + 1) tile_store(Cn[(s + 1) & 1] + ti * DIAG_TS, a);
+        }
+      } else if (inverse) {
+        // ---- X tile (ti, tk): add the term whose operands became final; finish two steps after row ti of L ----
+        const int k = (s == tk + 2) ? tk : s - 3;
+        if ((s == tk + 2) || (k > tk && k < ti)) {
+          double l[4][4], x[4][4];
+          tile_load(Lt + diag_tile(ti, k) * DIAG_TS, l);
+          tile_load(Xt + diag_tile(k, tk) * DIAG_TS, x);
+          tile_add_ab(a, l, x);
+        }
+        if (s == ti + 2) {
+          double xd[4][4], x[4][4];
+          tile_load(Xt + diag_tile(ti, ti) * DIAG_TS, xd);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              double acc = 0.0;
+#pragma unroll
+              for (int m = 0; m <= r; ++m) acc = fma(-xd[r][m], a[m][q], acc);
+              x[r][q] = acc;
+            }
+          tile_store(Xt + diag_tile(ti, tk) * DIAG_TS, x);
+        }
+      } else if (tid == DIAG_HELPER && s > 0 && s <= DIAG_NT) {
+        // ---- diagonal tiles of L and of X for column s-1, pivot check ----
+        const int j = s - 1;
+        const double* g = &Dg[j][0];
+        const double l10 = g[0], l20 = g[1], l30 = g[2], l21 = g[3], l31 = g[4], l32 = g[5];
+        const double d0 = g[6], d1 = g[7], d2 = g[8], d3 = g[9];
+        const double i00 = g[10], i11 = g[11], i22 = g[12], i33 = g[13];
+        int first_bad = 0;                     // d = q rsqrt(q) is positive exactly when the pivot q is
+        if (!(d3 > 0.0)) first_bad = 4;
+        if (!(d2 > 0.0)) first_bad = 3;
+        if (!(d1 > 0.0)) first_bad = 2;
+        if (!(d0 > 0.0)) first_bad = 1;
+        if (first_bad) atomicCAS(&status[b], 0, r0 + 4 * j + first_bad);
+        double t[4][4];
+        t[0][0] = d0;  t[0][1] = 0.0; t[0][2] = 0.0; t[0][3] = 0.0;
+        t[1][0] = l10; t[1][1] = d1;  t[1][2] = 0.0; t[1][3] = 0.0;
+        t[2][0] = l20; t[2][1] = l21; t[2][2] = d2;  t[2][3] = 0.0;
+        t[3][0] = l30; t[3][1] = l31; t[3][2] = l32; t[3][3] = d3;
+        tile_store(Lt + diag_tile(j, j) * DIAG_TS, t);
         const double i10 = -l10 * i00 * i11;
         const double i21 = -l21 * i11 * i22;
         const double i32 = -l32 * i22 * i33;
         const double i20 = -(l20 * i00 + l21 * i10) * i22;
         const double i31 = -(l31 * i11 + l32 * i21) * i33;
         const double i30 = -(l30 * i00 + l31 * i10 + l32 * i20) * i33;
-        double* xd = &Xd[jb][0];
-        xd[0] = i00; xd[1] = 0.0; xd[2] = 0.0; xd[3] = 0.0;
-        xd[4] = i10; xd[5] = i11; xd[6] = 0.0; xd[7] = 0.0;
-        xd[8] = i20; xd[9] = i21; xd[10] = i22; xd[11] = 0.0;
-        xd[12] = i30; xd[13] = i31; xd[14] = i32; xd[15] = i33;
-      } else {                               // below the diagonal: X = C Ld^-T, final, and published for the updates
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const double c0 = a[r][0], c1 = a[r][1], c2 = a[r][2], c3 = a[r][3];
-          const double x0 = c0 * rs0;
-          const double x1 = fma(-x0, l10, c1) * rs1;
-          const double x2 = fma(-x1, l21, fma(-x0, l20, c2)) * rs2;
-          const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, c3))) * rs3;
-          a[r][0] = x0; a[r][1] = x1; a[r][2] = x2; a[r][3] = x3;
-          *reinterpret_cast<double2*>(&Xb[ti][4 * r]) = make_double2(x0, x1);
-          *reinterpret_cast<double2*>(&Xb[ti][4 * r + 2]) = make_double2(x2, x3);
-        }
+        t[0][0] = i00;
+        t[1][0] = i10; t[1][1] = i11;
+        t[2][0] = i20; t[2][1] = i21; t[2][2] = i22;
+        t[3][0] = i30; t[3][1] = i31; t[3][2] = i32; t[3][3] = i33;
+        tile_store(Xt + diag_tile(j, j) * DIAG_TS, t);
       }
     }
     __syncthreads();
-    if (active && tk > jb) {
-      double xi[4][4], xk[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const double2 u0 = *reinterpret_cast<const double2*>(&Xb[ti][4 * r]);
-        const double2 u1 = *reinterpret_cast<const double2*>(&Xb[ti][4 * r + 2]);
-        xi[r][0] = u0.x; xi[r][1] = u0.y; xi[r][2] = u1.x; xi[r][3] = u1.y;
-        const double2 w0 = *reinterpret_cast<const double2*>(&Xb[tk][4 * r]);
-        const double2 w1 = *reinterpret_cast<const double2*>(&Xb[tk][4 * r + 2]);
-        xk[r][0] = w0.x; xk[r][1] = w0.y; xk[r][2] = w1.x; xk[r][3] = w1.y;
-      }
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          double sacc = a[ii][kk];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) sacc = fma(-xi[ii][c], xk[kk][c], sacc);
-          a[ii][kk] = sacc;
-        }
-    }
-    // Xb is rewritten only after the next column's barrier (A), which every reader of this column has passed
   }
   DIAG_MARK(1)
-  // ---- factor -> shared memory (zeros above the diagonal) and back to global ----
-#pragma unroll
-  for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int r = 4 * ti + ii, c = 4 * tk + kk;
-      const double v = (active && c <= r) ? a[ii][kk] : 0.0;
-      Ls[r][c] = v;
-      Xs[r][c] = 0.0;
-      if (active && c <= r && r < bs) Lp[(long long)r * L.ld + c] = v;
-    }
-  __syncthreads();
-  if (tid == 0 && bad) atomicCAS(&status[b], 0, bad);
-  DIAG_MARK(2)
-  // ---- inverse X = L^-1: 4 x 4 diagonal tiles (computed with the factor), then X21 = -X22 (L21 X11) level by level ----
-  if (tid < NB * 4) {
-    const int t4 = tid >> 4, e = tid & 15;
-    Xs[4 * t4 + (e >> 2)][4 * t4 + (e & 3)] = Xd[t4][e];
-  }
-  __syncthreads();
-  diag_inverse_level<4>(Ls, Xs, Ts, tid);
-  diag_inverse_level<8>(Ls, Xs, Ts, tid);
-  diag_inverse_level<16>(Ls, Xs, Ts, tid);
-  diag_inverse_level<32>(Ls, Xs, Ts, tid);
-  DIAG_MARK(3)
-  // publish: dinv block [NB x NB] row-major with explicit zeros above the diagonal / outside bs
+  // ---- results to global memory: tile (r, c) of the 16 x 16 tile grid per thread ----
   double* dp = dinv + ((long long)b * nblk + blk) * (NB * NB);
-  for (int e = tid; e < NB * NB; e += DIAG_THREADS) {
-    const int r = e / NB, cc = e % NB;
-    dp[e] = (r < bs && cc < bs) ? Xs[r][cc] : 0.0;
-  }
-  if (has_linv) {
-    double* ip = linv.p + (long long)b * linv.stride + (long long)r0 * linv.ld + r0;
-    for (int e = tid; e < bs * NB; e += DIAG_THREADS) {
-      const int r = e / NB, cc = e % NB;
-      if (cc < bs) ip[(long long)r * linv.ld + cc] = (cc <= r) ? Xs[r][cc] : Xs[cc][r];
+  double* ip = has_linv ? linv.p + (long long)b * linv.stride + (long long)r0 * linv.ld + r0 : nullptr;
+  if (tid < DIAG_NT * DIAG_NT) {
+    const int r = tid >> 4, c = tid & 15;
+    double t[4][4];
+    if (r > c) {
+      tile_load(Lt + diag_tile(r, c) * DIAG_TS, t);
+      tile_to_global(Lp, L.ld, 4 * r, 4 * c, bs, t, false, false);
+      tile_load(Xt + diag_tile(r, c) * DIAG_TS, t);
+      tile_to_global(dp, NB, 4 * r, 4 * c, bs, t, false, true);
+      if (ip) tile_to_global(ip, linv.ld, 4 * r, 4 * c, bs, t, false, false);
+    } else if (r == c) {
+      tile_load(Lt + diag_tile(r, r) * DIAG_TS, t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)              // the strict upper triangle of the matrix buffer is scratch of the inverse
+#pragma unroll
+        for (int q = 0; q <= i; ++q)
+          if (4 * r + i < bs) Lp[(long long)(4 * r + i) * L.ld + 4 * r + q] = t[i][q];
+      tile_load(Xt + diag_tile(r, r) * DIAG_TS, t);
+      tile_to_global(dp, NB, 4 * r, 4 * r, bs, t, false, true);
+      if (ip) {
+        t[0][1] = t[1][0]; t[0][2] = t[2][0]; t[0][3] = t[3][0]; t[1][2] = t[2][1]; t[1][3] = t[3][1]; t[2][3] = t[3][2];
+        tile_to_global(ip, linv.ld, 4 * r, 4 * r, bs, t, false, false);
+      }
+    } else {
+      if (ip) {                                // mirrored copy of X above the diagonal
+        tile_load(Xt + diag_tile(c, r) * DIAG_TS, t);
+        tile_to_global(ip, linv.ld, 4 * r, 4 * c, bs, t, true, false);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[i][q] = 0.0;
+      tile_to_global(dp, NB, 4 * r, 4 * c, bs, t, false, true);
     }
   }
   DIAG_MARK(4)
@@ -663,14 +773,6 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
   MatView none{nullptr, 0, 0};
   MatView lv = linv ? *linv : none;
   Operand opL{L, plan.rows, plan.n}, opD{dv, plan.nblk * NB, NB};
-  constexpr size_t DIAG_SMEM = 2 * NB * (NB + 1) * sizeof(double);
-  static bool diag_attr[64] = {false};
-  int dev = 0;
-  SPW_CUDA(cudaGetDevice(&dev));
-  if (!diag_attr[dev & 63]) {
-    SPW_CUDA(cudaFuncSetAttribute(diag_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-    diag_attr[dev & 63] = true;
-  }
   const int per_outer = OUTER_W / NB;
   const int nouter = (int)plan.outer.size();
   // SPW_POTRF_PROFILE=1: CUDA-event timing of the four kinds of launches (diagnostic; serialises nothing extra)
@@ -686,8 +788,8 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
   const bool ahead = la && la->bulk && (int)la->ev_chain.size() >= nouter && (int)la->ev_bulk.size() >= nouter && nouter > 2;
   for (int j = 0; j < plan.nblk; ++j) {
     mark();
-    diag_factor_kernel<<<batch, DIAG_THREADS, DIAG_SMEM, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
-                                                               g_diag_dbg);
+    diag_factor_kernel<<<batch, DIAG_THREADS, 0, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
+                                                       g_diag_dbg);
     SPW_LAUNCHED();
     mark();
     SPW_TRY(launch_gemm_tasks(plan.shape_panel, plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, opL, opD,
