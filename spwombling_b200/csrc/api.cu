@@ -114,21 +114,30 @@ static int get_ctx(DeviceCtx** out) {
 // lookahead resources for factorising one matrix of order n (nullptr when disabled by SPW_LOOKAHEAD=0)
 static int get_lookahead(DeviceCtx& c, int n, Lookahead** out) {
   *out = nullptr;
+  // SPW_LOOKAHEAD: 0 plain right-looking schedule; 1 bulk of each trailing update concurrent with the next panel;
+  // 2 / 3 (default 3) pieces of the bulk in the shadow of the diagonal-block kernels (see potrf_batched)
   const char* env = getenv("SPW_LOOKAHEAD");
-  if (!(env && env[0] == '1')) return SPW_OK;   // opt-in until verified on the GPU
+  const int mode = (env && env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
+  if (mode == 0) return SPW_OK;
   std::lock_guard<std::mutex> lk(g_ctx_mu);
+  c.la.mode = mode;
   if (!c.la.bulk) {
     int lo = 0, hi = 0;
     SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&c.la.bulk, cudaStreamNonBlocking, lo));   // lowest priority: bulk work
   }
-  const size_t need = (size_t)ceil_div(n, OUTER_W) + 1;
+  const size_t need = (size_t)ceil_div(n, c.la.mode >= 2 ? NB : OUTER_W) + 1;
   while (c.la.ev_chain.size() < need) {
     cudaEvent_t a, b;
     SPW_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
     SPW_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     c.la.ev_chain.push_back(a);
     c.la.ev_bulk.push_back(b);
+  }
+  while (c.la.ev_aux.size() < (size_t)ceil_div(n, OUTER_W) + 1) {
+    cudaEvent_t a;
+    SPW_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    c.la.ev_aux.push_back(a);
   }
   *out = &c.la;
   return SPW_OK;
@@ -582,6 +591,8 @@ int spw_shutdown(void) {
     c.la.bulk = nullptr;
     for (auto e : c.la.ev_chain) cudaEventDestroy(e);
     for (auto e : c.la.ev_bulk) cudaEventDestroy(e);
+    for (auto e : c.la.ev_aux) cudaEventDestroy(e);
+    c.la.ev_aux.clear();
     c.la.ev_chain.clear();
     c.la.ev_bulk.clear();
   }

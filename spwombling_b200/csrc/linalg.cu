@@ -573,7 +573,7 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   // machine with 128 x 64 tiles everywhere
   plan.shape_panel = single ? 2 : 1;
   plan.shape_inner = single ? 2 : 1;
-  plan.shape_outer = 1;
+  plan.shape_outer = single ? 2 : 1;     // one matrix: 64 x 64 tiles keep the tail of every launch short
   std::vector<GemmTask> tasks;
   const int T = 128;   // tile edge of the triangular-inverse products (shape L)
   plan.panel.resize(plan.nblk);
@@ -581,6 +581,8 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   plan.outer.clear();
   plan.outer_next.clear();
   plan.outer_bulk.clear();
+  plan.outer_first.clear();
+  plan.outer_rest.clear();
   int pm, pn, im, in_, om, on;
   shape_dims(plan.shape_panel, pm, pn);
   shape_dims(plan.shape_inner, im, in_);
@@ -624,14 +626,19 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
     // outer trailing update: C[I][K] -= L[I][J0:J1] * L[K][J0:J1]^T for the lower triangle right of the outer block;
     // listed as two consecutive groups -- the columns of the NEXT outer block first (what the next panel needs), then
     // the rest (the bulk a lookahead schedule runs concurrently with the next panel)
-    ChunkRange o, oa, ob;
-    o.begin = oa.begin = (int)tasks.size();
-    for (int part = 0; part < 2; ++part) {
-      if (part == 1) ob.begin = (int)tasks.size();
+    // listed as three consecutive groups: the first 64 columns of the NEXT outer block (what its first step needs),
+    // the other columns of that block (needed from its first in-block update on), and the rest (the bulk)
+    ChunkRange o, oa, ob, of, orr;
+    o.begin = oa.begin = of.begin = (int)tasks.size();
+    const int strip = std::max(on, NB);
+    for (int part = 0; part < 3; ++part) {
+      if (part == 1) orr.begin = (int)tasks.size();
+      if (part == 2) ob.begin = (int)tasks.size();
       for (int r = J1; r < plan.rows; r += om) {
         const int m = std::min(om, plan.rows - r);
         for (int c = J1; c < n && c <= r + m - 1; c += on) {
-          if ((c < J1 + OUTER_W) != (part == 0)) continue;
+          const int p = (c < J1 + strip) ? 0 : (c < J1 + OUTER_W) ? 1 : 2;
+          if (p != part) continue;
           GemmTask t = blank_task();
           t.a_row = r; t.a_col = J0;
           t.b_row = c; t.b_col = J0;
@@ -641,13 +648,19 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
           tasks.push_back(t);
         }
       }
-      if (part == 0) oa.count = (int)tasks.size() - oa.begin;
+      if (part == 0) of.count = (int)tasks.size() - of.begin;
+      if (part == 1) {
+        orr.count = (int)tasks.size() - orr.begin;
+        oa.count = (int)tasks.size() - oa.begin;
+      }
     }
     ob.count = (int)tasks.size() - ob.begin;
     o.count = (int)tasks.size() - o.begin;
     plan.outer.push_back(o);
     plan.outer_next.push_back(oa);
     plan.outer_bulk.push_back(ob);
+    plan.outer_first.push_back(of);
+    plan.outer_rest.push_back(orr);
   }
   // triangular inverse levels: s = NB, 2NB, ... ; pairs (block1 = [o, o+s), block2 = [o+s, min(o+2s, n)))
   for (int s = NB; s < n; s *= 2) {
@@ -785,22 +798,84 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     cudaEventRecord(e, st);
     evs.push_back(e);
   };
-  const bool ahead = la && la->bulk && (int)la->ev_chain.size() >= nouter && (int)la->ev_bulk.size() >= nouter && nouter > 2;
+  const bool ahead = la && la->mode == 1 && la->bulk && (int)la->ev_chain.size() >= nouter &&
+                     (int)la->ev_bulk.size() >= nouter && nouter > 2;
+  // Shadow schedule (modes 2 and 3, one matrix): the trailing update of outer block m is cut in three.  Only the
+  // first 64 columns of block m+1 are updated on the main stream before its first step.  The other columns of block
+  // m+1 start with its first diagonal-block kernel on the second stream (the first in-block update waits for them),
+  // followed by the bulk (columns beyond block m+1, no tile in common with the steps of block m+1), which is cut
+  // into one piece per step: piece i starts together with the single-CTA diagonal-block kernel of step i, so the
+  // other SMs have work while that kernel runs.  Mode 2: the panel product of the step waits for the piece (the
+  // small kernels never compete with bulk CTAs); mode 3: only the next trailing update waits (work-conserving;
+  // faster with 64 x 64 tiles, whose CTAs free their SM within a few microseconds).
+  const bool shadow = la && la->mode >= 2 && la->bulk && batch == 1 && (int)la->ev_chain.size() >= plan.nblk &&
+                      (int)la->ev_bulk.size() >= plan.nblk && (int)la->ev_aux.size() >= nouter && nouter > 2;
+  int sm_count = 148, pending = -1;   // pending: last piece the main stream has not waited for (mode 3)
+  // the cross-stream edges cost a few microseconds each: a trailing update with little bulk runs unsplit instead
+  static const int shadow_min = getenv("SPW_SHADOW_MIN") ? atoi(getenv("SPW_SHADOW_MIN")) : 300;
+  auto split = [&](int m) { return shadow && m >= 0 && m < nouter && plan.outer_bulk[m].count >= shadow_min; };
+  if (shadow) {
+    int dev = 0;
+    SPW_CUDA(cudaGetDevice(&dev));
+    SPW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   for (int j = 0; j < plan.nblk; ++j) {
     mark();
+    const int mb = j / per_outer;                      // outer block of this step
+    if (split(mb - 1)) SPW_CUDA(cudaEventRecord(la->ev_chain[j], st));
     diag_factor_kernel<<<batch, DIAG_THREADS, 0, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
                                                        g_diag_dbg);
     SPW_LAUNCHED();
+    bool rest_wait = false;
+    if (split(mb - 1)) {
+      const ChunkRange& ob = plan.outer_bulk[mb - 1];
+      const ChunkRange& orr = plan.outer_rest[mb - 1];
+      const int steps = std::min(per_outer, plan.nblk - mb * per_outer), i = j - mb * per_outer;
+      bool forked = false;
+      if (i == 0 && orr.count > 0) {            // the columns the first in-block update of this block touches
+        SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + orr.begin, orr.count, batch, opL, opL, L, none, -1.0,
+                                  la->bulk));
+        SPW_CUDA(cudaEventRecord(la->ev_aux[mb], la->bulk));
+        forked = rest_wait = true;
+      }
+      // piece i of bulk(mb - 1): whole waves of tiles where the bulk is large
+      const int wave = 2 * (sm_count - 1);             // tiles resident next to the diagonal-block CTA
+      int per = (ob.count + steps - 1) / steps;
+      if (ob.count >= steps * wave) per = (ob.count / wave / steps) * wave;
+      const int b0 = std::min(ob.count, i * per), b1 = (i == steps - 1) ? ob.count : std::min(ob.count, (i + 1) * per);
+      if (b1 > b0) {
+        if (!forked) SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin + b0, b1 - b0, batch, opL, opL, L, none, -1.0,
+                                  la->bulk));
+        forked = true;
+      }
+      if (forked) {
+        SPW_CUDA(cudaEventRecord(la->ev_bulk[j], la->bulk));
+        if (la->mode == 2) {
+          SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[j], 0));
+          rest_wait = false;
+        } else {
+          pending = j;
+        }
+      }
+    }
     mark();
     SPW_TRY(launch_gemm_tasks(plan.shape_panel, plan.d_tasks + plan.panel[j].begin, plan.panel[j].count, batch, opL, opD,
                               L, none, 1.0, st));
     mark();
+    if (rest_wait) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_aux[mb], 0));
     SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
                               L, none, -1.0, st));
     mark();
     if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
       const int m = j / per_outer;
-      if (!ahead) {
+      if (shadow) {
+        if (pending >= 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[pending], 0));
+        pending = -1;
+        const ChunkRange& oa = split(m) ? plan.outer_first[m] : plan.outer[m];
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+      } else if (!ahead) {
         const ChunkRange& o = plan.outer[m];
         SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
       } else {

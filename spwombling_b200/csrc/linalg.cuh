@@ -38,6 +38,7 @@ struct LinalgPlan {
   std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
   std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
   std::vector<ChunkRange> outer_next, outer_bulk;   // the same tasks split: next outer block's columns / the rest
+  std::vector<ChunkRange> outer_first, outer_rest;  // outer_next split again: its first 64 columns / the others
   std::vector<ChunkRange> inv1, inv2;           // per trtri level
   ChunkRange prod{0, 0};                        // T^T T of an inverted factor (spsample)
   GemmTask* d_tasks = nullptr;
@@ -58,7 +59,10 @@ void plan_free(LinalgPlan& plan);
 // Optional lookahead schedule (single-matrix chains): a second stream and per-outer-block events.
 struct Lookahead {
   cudaStream_t bulk = nullptr;
-  std::vector<cudaEvent_t> ev_chain, ev_bulk;
+  int mode = 1;   // 1: bulk of each trailing update concurrent with the next panel; 2: bulk cut into pieces that run in
+                  // the shadow of the single-CTA diagonal-block kernels of the next outer block
+  std::vector<cudaEvent_t> ev_chain, ev_bulk;   // mode 1: one pair per outer block; modes 2, 3: one pair per 64-wide step
+  std::vector<cudaEvent_t> ev_aux;              // modes 2, 3: one per outer block
 };
 int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv, int batch, int* status,
                   cudaStream_t st, Lookahead* la = nullptr);
