@@ -196,83 +196,62 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
   }
   __syncthreads();
   const int total_steps = 1 + 3 * c.niter;              // initial factorisation + 3 proposals per iteration
+  if (tid == 0) hlm_propose(s, c, -1, norm);
+  __syncthreads();
   for (int step = 0; step < total_steps; ++step) {
     const int p = (step == 0) ? -1 : (step - 1) % 3;
-    if (tid == 0) hlm_propose(s, c, p, norm);
-    __syncthreads();
     const double ph = s.prop[2], s2 = s.prop[0], t2 = s.prop[1];
-    // ---- assemble all tiles ----
-    for (int e = tid; e < ntiles; e += HLM_SMALL_THREADS) {
+    // ---- assemble all tiles, one element per thread and pass (tiles are stored in list order: column by column) ----
+    for (int idx = tid; idx < ntiles * 16; idx += HLM_SMALL_THREADS) {
+      const int e = idx >> 4, r = (idx >> 2) & 3, cc = idx & 3;
       const int ti = tl[e] >> 8, tk = tl[e] & 255;
-      double a[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int i = 4 * ti + r, k = 4 * tk + cc;
-          double v = 0.0;
-          if (ti == NC) {                               // the y tile row: y^T in its first row
-            if (r == 0 && k < n) v = syv[k];
-          } else if (i >= n || k >= n) {
-            v = (i == k) ? 1.0 : 0.0;                   // identity padding
-          } else if (i == k) {
-            v = s2 + t2;
-          } else if (k < i) {
-            const double dx = sx[i] - sx[k], dy = sy[i] - sy[k];
-            const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            v = s2 * cov_rho<TYPE>(ph, d);
-          }
-          a[r][cc] = v;
-        }
-      tile_store(T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS, a);
+      const int i = 4 * ti + r, k = 4 * tk + cc;
+      double v = 0.0;
+      if (ti == NC) {                                   // the y tile row: y^T in its first row
+        if (r == 0 && k < n) v = syv[k];
+      } else if (i >= n || k >= n) {
+        v = (i == k) ? 1.0 : 0.0;                       // identity padding
+      } else if (i == k) {
+        v = s2 + t2;
+      } else if (k < i) {
+        const double dx = sx[i] - sx[k], dy = sy[i] - sy[k];
+        const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        v = s2 * cov_rho<TYPE>(ph, d);
+      }
+      T[(size_t)e * HLM_TS + 4 * r + cc] = v;
     }
     __syncthreads();
-    // ---- factorisation: NC tile columns, ONE barrier each.  In step jb the "owner" threads (one per tile of tile
-    //      column jb) first apply the pending update of column jb - 1 to their own tile and to a private copy of the
-    //      pivot tile, then factor / solve (their tiles are final after this step); meanwhile the worker threads apply
-    //      the update of column jb - 1 to all tiles right of column jb. ----
-    for (int jb = 0; jb < NC; ++jb) {
-      if (tid < NR - jb) {
+    // ---- factorisation: NC tile columns, ONE barrier each.  In step jb the "owner" lanes (one per tile of tile
+    //      column jb: warp 0, and warp 1 while more than 32 tile rows remain) first apply the pending update of
+    //      column jb - 1 to the pivot tile and to their own tile, then factor / solve (their tiles are final after
+    //      this step); meanwhile the worker warps apply the update of column jb - 1 to all tiles right of column jb.
+    //      The step time is the owners' dependent FP64 chain, so their path is uniform and the warps that share a
+    //      scheduler with an owner warp (warp & 3 == 0, resp. <= 1) stay idle. ----
+    int base_prev = 0, base_cur = 0;                      // first tile of tile columns jb - 1 and jb (== tstart[])
+    for (int jb = 0; jb < NC; base_prev = base_cur, base_cur += NR - jb, ++jb) {
+      const int nown = (NR - jb > 32) ? 2 : 1;
+      const int warp = tid >> 5;
+      if (warp < nown) {
         const int ti = jb + tid;
-        double D[4][4], xk[4][4];
-        tile_load(T + (size_t)(jb * (jb + 1) / 2 + jb) * HLM_TS, D);
-        if (jb > 0) {
-          tile_load(T + (size_t)(jb * (jb + 1) / 2 + jb - 1) * HLM_TS, xk);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int cc = 0; cc <= r; ++cc) {
-              double acc = D[r][cc];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) acc = fma(-xk[r][k], xk[cc][k], acc);
-              D[r][cc] = acc;
-            }
-        }
-        const double q0 = D[0][0], rs0 = fast_rsqrt(q0);
-        const double l10 = D[1][0] * rs0, l20 = D[2][0] * rs0, l30 = D[3][0] * rs0;
-        const double q1 = fma(-l10, l10, D[1][1]), rs1 = fast_rsqrt(q1);
-        const double l21 = fma(-l20, l10, D[2][1]) * rs1, l31 = fma(-l30, l10, D[3][1]) * rs1;
-        const double q2 = fma(-l21, l21, fma(-l20, l20, D[2][2])), rs2 = fast_rsqrt(q2);
-        const double l32 = fma(-l31, l21, fma(-l30, l20, D[3][2])) * rs2;
-        const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[3][3]))), rs3 = fast_rsqrt(q3);
-        if (tid == 0) {
-          int first_bad = 0;
-          if (!(q3 > 0.0)) first_bad = 4;
-          if (!(q2 > 0.0)) first_bad = 3;
-          if (!(q1 > 0.0)) first_bad = 2;
-          if (!(q0 > 0.0)) first_bad = 1;
-          if (first_bad && bad == 0) bad = 4 * jb + first_bad;
-          diagv[4 * jb + 0] = q0 * rs0;
-          diagv[4 * jb + 1] = q1 * rs1;
-          diagv[4 * jb + 2] = q2 * rs2;
-          diagv[4 * jb + 3] = q3 * rs3;
-        } else {
-          double* tp = T + (size_t)(ti * (ti + 1) / 2 + jb) * HLM_TS;
-          double C[4][4];
-          tile_load(tp, C);
+        if (ti < NR) {
+          const double* colp = T + (size_t)base_cur * HLM_TS;                   // tile (jb + i, jb) at colp + i * TS
+          double D[4][4], C[4][4];
+          tile_load(colp, D);
+          tile_load(colp + (size_t)tid * HLM_TS, C);
           if (jb > 0) {
-            double xi[4][4];
-            tile_load(T + (size_t)(ti * (ti + 1) / 2 + jb - 1) * HLM_TS, xi);
+            const double* prevp = T + (size_t)(base_prev + 1) * HLM_TS;        // tile (jb + i, jb - 1) at prevp + i * TS
+            double xk[4][4], xi[4][4];
+            tile_load(prevp, xk);
+            tile_load(prevp + (size_t)tid * HLM_TS, xi);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int cc = 0; cc <= r; ++cc) {
+                double acc = D[r][cc];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma(-xk[r][k], xk[cc][k], acc);
+                D[r][cc] = acc;
+              }
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -283,25 +262,45 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
                 C[r][cc] = acc;
               }
           }
+          const double q0 = D[0][0], rs0 = fast_rsqrt(q0);
+          const double l10 = D[1][0] * rs0, l20 = D[2][0] * rs0, l30 = D[3][0] * rs0;
+          const double q1 = fma(-l10, l10, D[1][1]), rs1 = fast_rsqrt(q1);
+          const double l21 = fma(-l20, l10, D[2][1]) * rs1, l31 = fma(-l30, l10, D[3][1]) * rs1;
+          const double q2 = fma(-l21, l21, fma(-l20, l20, D[2][2])), rs2 = fast_rsqrt(q2);
+          const double l32 = fma(-l31, l21, fma(-l30, l20, D[3][2])) * rs2;
+          const double q3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, D[3][3]))), rs3 = fast_rsqrt(q3);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < 4; ++r) {        // X = C Ld^-T (idle work on the pivot tile's own lane)
             const double x0 = C[r][0] * rs0;
             const double x1 = fma(-x0, l10, C[r][1]) * rs1;
             const double x2 = fma(-x1, l21, fma(-x0, l20, C[r][2])) * rs2;
             const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, C[r][3]))) * rs3;
             C[r][0] = x0; C[r][1] = x1; C[r][2] = x2; C[r][3] = x3;
           }
-          tile_store(tp, C);
+          if (tid == 0) {
+            int first_bad = 0;
+            if (!(q3 > 0.0)) first_bad = 4;
+            if (!(q2 > 0.0)) first_bad = 3;
+            if (!(q1 > 0.0)) first_bad = 2;
+            if (!(q0 > 0.0)) first_bad = 1;
+            if (first_bad && bad == 0) bad = 4 * jb + first_bad;
+            *reinterpret_cast<double2*>(&diagv[4 * jb]) = make_double2(q0 * rs0, q1 * rs1);
+            *reinterpret_cast<double2*>(&diagv[4 * jb + 2]) = make_double2(q2 * rs2, q3 * rs3);
+          } else {
+            tile_store(T + (size_t)(base_cur + tid) * HLM_TS, C);
+          }
         }
-      } else if (tid >= 64 && jb > 0) {
+      } else if ((warp & 3) >= nown && jb > 0) {
         // workers: rank-4 update with column jb - 1 of every tile (ti, tk), tk > jb
-        const int jp = jb - 1;
-        for (int e = tstart[jb + 1] + (tid - 64); e < ntiles; e += HLM_SMALL_THREADS - 64) {
+        const int nwork = (4 - nown) * 4 * 32;
+        const int widx = ((warp >> 2) * (4 - nown) + (warp & 3) - nown) * 32 + (tid & 31);
+        const double* prevp = T + (size_t)(base_prev - (jb - 1)) * HLM_TS;     // tile (i, jb - 1) at prevp + i * TS
+        for (int e = base_cur + NR - jb + widx; e < ntiles; e += nwork) {
           const int ti = tl[e] >> 8, tk = tl[e] & 255;
           double xi[4][4], xk[4][4], a[4][4];
-          tile_load(T + (size_t)(ti * (ti + 1) / 2 + jp) * HLM_TS, xi);
-          tile_load(T + (size_t)(tk * (tk + 1) / 2 + jp) * HLM_TS, xk);
-          double* tp = T + (size_t)(ti * (ti + 1) / 2 + tk) * HLM_TS;
+          tile_load(prevp + (size_t)ti * HLM_TS, xi);
+          tile_load(prevp + (size_t)tk * HLM_TS, xk);
+          double* tp = T + (size_t)e * HLM_TS;
           tile_load(tp, a);
 #pragma unroll
           for (int r = 0; r < 4; ++r)
@@ -321,7 +320,7 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
     double sl = 0.0, sq = 0.0;
     for (int j = tid; j < n; j += HLM_SMALL_THREADS) {
       sl += log(diagv[j]);
-      const double w = T[(size_t)(NC * (NC + 1) / 2 + (j >> 2)) * HLM_TS + (j & 3)];   // row 0 of the y tile row
+      const double w = T[(size_t)(tstart[j >> 2] + NC - (j >> 2)) * HLM_TS + (j & 3)];   // row 0 of the y tile row
       sq = fma(w, w, sq);
     }
     sl = warp_sum(sl);
@@ -340,6 +339,7 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
       s.logdet_p = al;
       s.quad_p = aq;
       hlm_accept(s, c, p, unif, o);
+      if (step + 1 < total_steps) hlm_propose(s, c, step % 3, norm);      // the next proposal, in the same serial section
     }
     __syncthreads();
   }
@@ -378,7 +378,7 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
   SPW_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(int), st));
   {
     // default for n <= HLM_SMALL_DEFAULT_MAX, where the single-CTA chain beats the blocked multi-kernel path replayed as a
-    // CUDA graph (12.0k vs 5.1k it/s at n = 100, 5.6k vs 3.7k at n = 155, 3.0k vs 2.8k at n = 200); SPW_HLM_SMALL=0 / 1
+    // CUDA graph (15.2k vs 5.1k it/s at n = 100, 6.8k vs 3.7k at n = 155, 4.0k vs 2.8k at n = 200); SPW_HLM_SMALL=0 / 1
     // forces the choice (1: up to HLM_SMALL_MAX)
     const char* env_small = getenv("SPW_HLM_SMALL");
     const bool allow_small = env_small ? (env_small[0] == '1') : (n <= HLM_SMALL_DEFAULT_MAX);
