@@ -138,3 +138,44 @@ def test_hlm_chain_blocked_path_vs_oracle():
         np.testing.assert_allclose(out["diagnostics"]["chain"][key], ref["chain"][key], rtol=1e-10)
     np.testing.assert_allclose(out["trgt_fn"], ref["trgt_fn"], rtol=1e-10)
     np.testing.assert_array_equal(out["diagnostics"]["accept_m"], ref["accept_m"])
+
+
+_SCHEDULE_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import spwombling_b200 as spw
+from oracle.hlm import hlm_bayes_sp, r_chol
+import oracle
+n, niter = 1100, 4
+rng = np.random.Generator(np.random.Philox(77))
+coords = rng.random((n, 2))
+y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
+y = y - y.mean()
+norm, unif = rng.standard_normal(3 * niter), rng.random(3 * niter)
+ref = hlm_bayes_sp(y, coords, niter=niter, nburn=1, report=2, cov_type="matern2", norm=norm, unif=unif, trgt_fn_compute=True)
+out = spw.hlmBayes_sp(y=y, coords=coords, niter=niter, nburn=1, report=2, cov_type="matern2", norm=norm, unif=unif,
+                      trgtFn_compute=True, verbose=False)
+for key in ("sig2", "tau2", "phi"):
+    np.testing.assert_allclose(out["diagnostics"]["chain"][key], ref["chain"][key], rtol=1e-10)
+np.testing.assert_allclose(out["trgt_fn"], ref["trgt_fn"], rtol=1e-10)
+A = oracle.cov_matern1(oracle.dist_matrix(coords), 8.0, 2.0) + 0.5 * np.eye(n)
+U, _ = spw.chol(A)
+Uo = r_chol(A)
+assert np.max(np.abs(U - Uo)) / np.max(np.abs(Uo)) < 1e-11
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
+def test_cholesky_schedules_against_oracle(mode):
+    """Every single-matrix Cholesky schedule (SPW_LOOKAHEAD 0..3; the switch is read once per process, hence the
+    subprocess) with the bulk split forced on at a size the oracle handles: ragged pieces, a partial last outer block
+    and the appended y row, against the reference's arithmetic."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPW_LOOKAHEAD=mode, SPW_SHADOW_MIN="1")
+    res = subprocess.run([sys.executable, "-c", _SCHEDULE_SCRIPT % {"root": root}], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-4000:]
