@@ -21,7 +21,9 @@ namespace spw {
 // (zero-filled by TMA), so the only masking left is the triangular one.
 //   L: 128 x 128, 3 stages, 1 CTA/SM   (long-k products of the triangular inverse)
 //   M: 128 x  64, 2 stages, 2 CTA/SM   (Cholesky panel / trailing updates: the second CTA hides the C read-modify-write)
-//   S:  64 x  64, 3 stages, 2 CTA/SM   (latency-critical panel steps of a single matrix)
+//   S:  64 x  64, 3 stages, 2 CTA/SM   (latency-critical steps and trailing updates of a single matrix)
+//   T:  32 x  64, 2 stages, 2 CTA/SM   (panel product of a single matrix: twice the CTAs; rows, not columns, are
+//                                       split because the product overwrites its own A operand)
 // ---------------------------------------------------------------------------------------------------
 namespace {
 constexpr int G_BK = 32, G_LDS = G_BK + 4, G_CW = 8, G_THREADS = 32 * G_CW;
@@ -37,6 +39,7 @@ struct GCfg {
 using GCfgL = GCfg<128, 128, 3, 1>;
 using GCfgM = GCfg<128, 64, 2, 2>;
 using GCfgS = GCfg<64, 64, 3, 2>;
+using GCfgT = GCfg<32, 64, 2, 2>;
 }  // namespace
 
 template <class Cfg>
@@ -560,7 +563,7 @@ static GemmTask blank_task() {
 }
 
 static void shape_dims(int shape, int& tm, int& tn) {
-  tm = (shape == 2) ? 64 : 128;
+  tm = (shape == 3) ? 32 : (shape == 2) ? 64 : 128;
   tn = (shape == 0) ? 128 : 64;
 }
 
@@ -571,7 +574,7 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   plan.nblk = ceil_div(n, NB);
   // tile shapes: a single matrix needs many small CTAs on the latency-critical 64-wide steps; batches fill the
   // machine with 128 x 64 tiles everywhere
-  plan.shape_panel = single ? 2 : 1;
+  plan.shape_panel = single ? 3 : 1;
   plan.shape_inner = single ? 2 : 1;
   plan.shape_outer = single ? 2 : 1;     // one matrix: 64 x 64 tiles keep the tail of every launch short
   std::vector<GemmTask> tasks;
@@ -770,12 +773,13 @@ static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand 
   return SPW_OK;
 }
 
-// shape: 0 = L (128 x 128), 1 = M (128 x 64), 2 = S (64 x 64); the task list must have been tiled accordingly
+// shape: 0 = L (128 x 128), 1 = M (128 x 64), 2 = S (64 x 64), 3 = T (32 x 64); the task list must have been tiled accordingly
 static int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
                              MatView CT, double alpha, cudaStream_t st, bool one_per_sm = false) {
   switch (shape) {
     case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
     case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
+    case 3: return launch_gemm_cfg<GCfgT>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
     default: return launch_gemm_cfg<GCfgS>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
   }
 }
