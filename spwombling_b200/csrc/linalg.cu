@@ -581,6 +581,7 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   const int T = 128;   // tile edge of the triangular-inverse products (shape L)
   plan.panel.resize(plan.nblk);
   plan.trail.resize(plan.nblk);
+  plan.trail_shape.assign(plan.nblk, plan.shape_inner);
   plan.outer.clear();
   plan.outer_next.clear();
   plan.outer_bulk.clear();
@@ -610,10 +611,19 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
         tasks.push_back(t);
       }
       plan.panel[j].count = (int)tasks.size() - plan.panel[j].begin;
-      // inner trailing update: columns of this outer block to the right of block j
+      // inner trailing update: columns of this outer block to the right of block j.  One matrix: when the 64-row
+      // tiles would leave more than half of the CTA slots empty, 32-row tiles are used instead
       plan.trail[j].begin = (int)tasks.size();
-      for (int r = r_begin; r < plan.rows; r += im) {
-        const int m = std::min(im, plan.rows - r);
+      int tim = im;
+      if (single) {
+        int cnt = 0;
+        for (int r = r_begin; r < plan.rows; r += im)
+          for (int c = r_begin; c < J1 && c <= r + std::min(im, plan.rows - r) - 1; c += in_) ++cnt;
+        if (cnt <= 148) tim = 32;
+      }
+      plan.trail_shape[j] = (tim == im) ? plan.shape_inner : 3;
+      for (int r = r_begin; r < plan.rows; r += tim) {
+        const int m = std::min(tim, plan.rows - r);
         for (int c = r_begin; c < J1 && c <= r + m - 1; c += in_) {
           GemmTask t = blank_task();
           t.a_row = r; t.a_col = c0;
@@ -869,7 +879,7 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
                               L, none, 1.0, st));
     mark();
     if (rest_wait) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_aux[mb], 0));
-    SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
+    SPW_TRY(launch_gemm_tasks(plan.trail_shape[j], plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
                               L, none, -1.0, st));
     mark();
     if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
