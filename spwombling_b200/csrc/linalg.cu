@@ -587,6 +587,7 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   plan.outer_bulk.clear();
   plan.outer_first.clear();
   plan.outer_rest.clear();
+  plan.outer_shape.clear();
   int pm, pn, im, in_, om, on;
   shape_dims(plan.shape_panel, pm, pn);
   shape_dims(plan.shape_inner, im, in_);
@@ -637,18 +638,24 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
       plan.trail[j].count = (int)tasks.size() - plan.trail[j].begin;
     }
     // outer trailing update: C[I][K] -= L[I][J0:J1] * L[K][J0:J1]^T for the lower triangle right of the outer block;
-    // listed as two consecutive groups -- the columns of the NEXT outer block first (what the next panel needs), then
-    // the rest (the bulk a lookahead schedule runs concurrently with the next panel)
     // listed as three consecutive groups: the first 64 columns of the NEXT outer block (what its first step needs),
     // the other columns of that block (needed from its first in-block update on), and the rest (the bulk)
     ChunkRange o, oa, ob, of, orr;
     o.begin = oa.begin = of.begin = (int)tasks.size();
     const int strip = std::max(on, NB);
+    int tom = om;                        // one matrix, few tiles left: 32-row tiles (twice the CTAs)
+    if (single) {
+      int cnt = 0;
+      for (int r = J1; r < plan.rows; r += om)
+        for (int c = J1; c < n && c <= r + std::min(om, plan.rows - r) - 1; c += on) ++cnt;
+      if (cnt <= 148) tom = 32;
+    }
+    plan.outer_shape.push_back(tom == om ? plan.shape_outer : 3);
     for (int part = 0; part < 3; ++part) {
       if (part == 1) orr.begin = (int)tasks.size();
       if (part == 2) ob.begin = (int)tasks.size();
-      for (int r = J1; r < plan.rows; r += om) {
-        const int m = std::min(om, plan.rows - r);
+      for (int r = J1; r < plan.rows; r += tom) {
+        const int m = std::min(tom, plan.rows - r);
         for (int c = J1; c < n && c <= r + m - 1; c += on) {
           const int p = (c < J1 + strip) ? 0 : (c < J1 + OUTER_W) ? 1 : 2;
           if (p != part) continue;
@@ -848,7 +855,7 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
       bool forked = false;
       if (i == 0 && orr.count > 0) {            // the columns the first in-block update of this block touches
         SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + orr.begin, orr.count, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[mb - 1], plan.d_tasks + orr.begin, orr.count, batch, opL, opL, L, none, -1.0,
                                   la->bulk));
         SPW_CUDA(cudaEventRecord(la->ev_aux[mb], la->bulk));
         forked = rest_wait = true;
@@ -860,7 +867,7 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
       const int b0 = std::min(ob.count, i * per), b1 = (i == steps - 1) ? ob.count : std::min(ob.count, (i + 1) * per);
       if (b1 > b0) {
         if (!forked) SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin + b0, b1 - b0, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[mb - 1], plan.d_tasks + ob.begin + b0, b1 - b0, batch, opL, opL, L, none, -1.0,
                                   la->bulk));
         forked = true;
       }
@@ -888,10 +895,10 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
         if (pending >= 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[pending], 0));
         pending = -1;
         const ChunkRange& oa = split(m) ? plan.outer_first[m] : plan.outer[m];
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
       } else if (!ahead) {
         const ChunkRange& o = plan.outer[m];
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
       } else {
         // Lookahead: the panel of outer block m is final.  The bulk of its trailing update (columns beyond the next
         // outer block) goes to the second stream, one CTA per SM so that the CTAs of the next panel's small kernels
@@ -903,11 +910,11 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
         SPW_CUDA(cudaEventRecord(la->ev_chain[m], st));
         SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[m], 0));
         static const bool bulk_one_per_sm = !(getenv("SPW_LA_WIDE") && getenv("SPW_LA_WIDE")[0] == '0');
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
                                   la->bulk, bulk_one_per_sm));
         SPW_CUDA(cudaEventRecord(la->ev_bulk[m], la->bulk));
         if (m > 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[m - 1], 0));
-        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
       }
     }
   }
