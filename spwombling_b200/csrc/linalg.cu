@@ -21,9 +21,9 @@ namespace spw {
 // (zero-filled by TMA), so the only masking left is the triangular one.
 //   L: 128 x 128, 3 stages, 1 CTA/SM   (long-k products of the triangular inverse)
 //   M: 128 x  64, 2 stages, 2 CTA/SM   (Cholesky panel / trailing updates: the second CTA hides the C read-modify-write)
-//   S:  64 x  64, 3 stages, 2 CTA/SM   (latency-critical steps and trailing updates of a single matrix)
-//   T:  32 x  64, 2 stages, 2 CTA/SM   (panel product of a single matrix: twice the CTAs; rows, not columns, are
-//                                       split because the product overwrites its own A operand)
+//   S:  64 x  64, 3 stages, 2 CTA/SM   (kept for experiments)
+//   T:  32 x  64, 2 stages, 3 CTA/SM   (every step of a single matrix: many short CTAs; for the panel product rows,
+//                                       not columns, are split because it overwrites its own A operand)
 // ---------------------------------------------------------------------------------------------------
 namespace {
 constexpr int G_BK = 32, G_LDS = G_BK + 4, G_CW = 8, G_THREADS = 32 * G_CW;
@@ -39,7 +39,7 @@ struct GCfg {
 using GCfgL = GCfg<128, 128, 3, 1>;
 using GCfgM = GCfg<128, 64, 2, 2>;
 using GCfgS = GCfg<64, 64, 3, 2>;
-using GCfgT = GCfg<32, 64, 2, 2>;
+using GCfgT = GCfg<32, 64, 2, 3>;
 }  // namespace
 
 template <class Cfg>
@@ -575,19 +575,18 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
   // tile shapes: a single matrix needs many small CTAs on the latency-critical 64-wide steps; batches fill the
   // machine with 128 x 64 tiles everywhere
   plan.shape_panel = single ? 3 : 1;
-  plan.shape_inner = single ? 2 : 1;
-  plan.shape_outer = single ? 2 : 1;     // one matrix: 64 x 64 tiles keep the tail of every launch short
+  plan.shape_inner = single ? 3 : 1;
+  plan.shape_outer = single ? 3 : 1;     // one matrix: small tiles keep the tail of every launch short and free their
+                                         // SM slot within microseconds (the shadow schedule depends on that)
   std::vector<GemmTask> tasks;
   const int T = 128;   // tile edge of the triangular-inverse products (shape L)
   plan.panel.resize(plan.nblk);
   plan.trail.resize(plan.nblk);
-  plan.trail_shape.assign(plan.nblk, plan.shape_inner);
   plan.outer.clear();
   plan.outer_next.clear();
   plan.outer_bulk.clear();
   plan.outer_first.clear();
   plan.outer_rest.clear();
-  plan.outer_shape.clear();
   int pm, pn, im, in_, om, on;
   shape_dims(plan.shape_panel, pm, pn);
   shape_dims(plan.shape_inner, im, in_);
@@ -612,19 +611,10 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
         tasks.push_back(t);
       }
       plan.panel[j].count = (int)tasks.size() - plan.panel[j].begin;
-      // inner trailing update: columns of this outer block to the right of block j.  One matrix: when the 64-row
-      // tiles would leave more than half of the CTA slots empty, 32-row tiles are used instead
+      // inner trailing update: columns of this outer block to the right of block j
       plan.trail[j].begin = (int)tasks.size();
-      int tim = im;
-      if (single) {
-        int cnt = 0;
-        for (int r = r_begin; r < plan.rows; r += im)
-          for (int c = r_begin; c < J1 && c <= r + std::min(im, plan.rows - r) - 1; c += in_) ++cnt;
-        if (cnt <= 148) tim = 32;
-      }
-      plan.trail_shape[j] = (tim == im) ? plan.shape_inner : 3;
-      for (int r = r_begin; r < plan.rows; r += tim) {
-        const int m = std::min(tim, plan.rows - r);
+      for (int r = r_begin; r < plan.rows; r += im) {
+        const int m = std::min(im, plan.rows - r);
         for (int c = r_begin; c < J1 && c <= r + m - 1; c += in_) {
           GemmTask t = blank_task();
           t.a_row = r; t.a_col = c0;
@@ -643,19 +633,11 @@ int plan_build(LinalgPlan& plan, int n, int extra_rows, int single) {
     ChunkRange o, oa, ob, of, orr;
     o.begin = oa.begin = of.begin = (int)tasks.size();
     const int strip = std::max(on, NB);
-    int tom = om;                        // one matrix, few tiles left: 32-row tiles (twice the CTAs)
-    if (single) {
-      int cnt = 0;
-      for (int r = J1; r < plan.rows; r += om)
-        for (int c = J1; c < n && c <= r + std::min(om, plan.rows - r) - 1; c += on) ++cnt;
-      if (cnt <= 148) tom = 32;
-    }
-    plan.outer_shape.push_back(tom == om ? plan.shape_outer : 3);
     for (int part = 0; part < 3; ++part) {
       if (part == 1) orr.begin = (int)tasks.size();
       if (part == 2) ob.begin = (int)tasks.size();
-      for (int r = J1; r < plan.rows; r += tom) {
-        const int m = std::min(tom, plan.rows - r);
+      for (int r = J1; r < plan.rows; r += om) {
+        const int m = std::min(om, plan.rows - r);
         for (int c = J1; c < n && c <= r + m - 1; c += on) {
           const int p = (c < J1 + strip) ? 0 : (c < J1 + OUTER_W) ? 1 : 2;
           if (p != part) continue;
@@ -855,19 +837,19 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
       bool forked = false;
       if (i == 0 && orr.count > 0) {            // the columns the first in-block update of this block touches
         SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[mb - 1], plan.d_tasks + orr.begin, orr.count, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + orr.begin, orr.count, batch, opL, opL, L, none, -1.0,
                                   la->bulk));
         SPW_CUDA(cudaEventRecord(la->ev_aux[mb], la->bulk));
         forked = rest_wait = true;
       }
       // piece i of bulk(mb - 1): whole waves of tiles where the bulk is large
-      const int wave = 2 * (sm_count - 1);             // tiles resident next to the diagonal-block CTA
+      const int wave = (plan.shape_outer == 3 ? GCfgT::MINB : 2) * (sm_count - 1);   // tiles resident next to the diagonal-block CTA
       int per = (ob.count + steps - 1) / steps;
       if (ob.count >= steps * wave) per = (ob.count / wave / steps) * wave;
       const int b0 = std::min(ob.count, i * per), b1 = (i == steps - 1) ? ob.count : std::min(ob.count, (i + 1) * per);
       if (b1 > b0) {
         if (!forked) SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[j], 0));
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[mb - 1], plan.d_tasks + ob.begin + b0, b1 - b0, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin + b0, b1 - b0, batch, opL, opL, L, none, -1.0,
                                   la->bulk));
         forked = true;
       }
@@ -886,7 +868,7 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
                               L, none, 1.0, st));
     mark();
     if (rest_wait) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_aux[mb], 0));
-    SPW_TRY(launch_gemm_tasks(plan.trail_shape[j], plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
+    SPW_TRY(launch_gemm_tasks(plan.shape_inner, plan.d_tasks + plan.trail[j].begin, plan.trail[j].count, batch, opL, opL,
                               L, none, -1.0, st));
     mark();
     if ((j + 1) % per_outer == 0 || j + 1 == plan.nblk) {
@@ -895,10 +877,10 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
         if (pending >= 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[pending], 0));
         pending = -1;
         const ChunkRange& oa = split(m) ? plan.outer_first[m] : plan.outer[m];
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
       } else if (!ahead) {
         const ChunkRange& o = plan.outer[m];
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + o.begin, o.count, batch, opL, opL, L, none, -1.0, st));
       } else {
         // Lookahead: the panel of outer block m is final.  The bulk of its trailing update (columns beyond the next
         // outer block) goes to the second stream, one CTA per SM so that the CTAs of the next panel's small kernels
@@ -910,11 +892,11 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
         SPW_CUDA(cudaEventRecord(la->ev_chain[m], st));
         SPW_CUDA(cudaStreamWaitEvent(la->bulk, la->ev_chain[m], 0));
         static const bool bulk_one_per_sm = !(getenv("SPW_LA_WIDE") && getenv("SPW_LA_WIDE")[0] == '0');
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + ob.begin, ob.count, batch, opL, opL, L, none, -1.0,
                                   la->bulk, bulk_one_per_sm));
         SPW_CUDA(cudaEventRecord(la->ev_bulk[m], la->bulk));
         if (m > 0) SPW_CUDA(cudaStreamWaitEvent(st, la->ev_bulk[m - 1], 0));
-        SPW_TRY(launch_gemm_tasks(plan.outer_shape[m], plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
+        SPW_TRY(launch_gemm_tasks(plan.shape_outer, plan.d_tasks + oa.begin, oa.count, batch, opL, opL, L, none, -1.0, st));
       }
     }
   }

@@ -35,8 +35,6 @@ struct LinalgPlan {
   int rows = 0;         // rows actually factored (n, or n + 1 for the augmented hlm system)
   int nblk = 0;
   int shape_panel = 1, shape_inner = 1, shape_outer = 1;   // GEMM tile shapes (0: 128x128, 1: 128x64, 2: 64x64, 3: 32x64)
-  std::vector<int> trail_shape;                 // per step: shape of its in-block update (shape_inner, or 3 when few tiles)
-  std::vector<int> outer_shape;                 // per outer block: shape of its trailing update (shape_outer, or 3)
   std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
   std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
   std::vector<ChunkRange> outer_next, outer_bulk;   // the same tasks split: next outer block's columns / the rest
