@@ -243,7 +243,12 @@ def test_hlm_kat(spw):
 
 @pytest.mark.parametrize("n,cov_type,niter,report", [(30, "matern2", 60, 10), (100, "matern1", 120, 20),
                                                      (100, "gaussian", 90, 30), (155, "matern2", 40, 10),
-                                                     (300, "matern2", 30, 10)])
+                                                     (300, "matern2", 30, 10),
+                                                     # single-CTA chain: degenerate sizes, the one / two owner-warp
+                                                     # boundary (n = 124 | 125) and the largest system it takes
+                                                     (1, "matern2", 12, 4), (2, "matern1", 12, 4), (5, "gaussian", 12, 4),
+                                                     (124, "matern2", 18, 6), (125, "matern1", 18, 6),
+                                                     (131, "gaussian", 18, 6), (200, "matern2", 15, 5)])
 def test_hlm_chain_vs_oracle(spw, n, cov_type, niter, report):
     rng = np.random.Generator(np.random.Philox(n + niter))
     coords = rng.random((n, 2))
