@@ -170,18 +170,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------------
 // Diagonal block: factor the bs x bs lower block (bs <= 64) and invert the factor in the same sweep.
-// The sweep is latency-bound on ONE warp's dependent FP64 chain (cycle probes: a lone warp issues a DFMA every
-// 2.1 cycles, a dependent one every 8.3, the reciprocal square root takes 49), so the design keeps that warp's
-// instruction stream minimal and divergence-free and gives every other job to other warps.  384 threads in 12 warps:
-//   * warp 0, lanes s..15: the owners of tile column s (4 pivots).  They read the column as published one step
-//     earlier, apply the pending rank-4 update of column s-1 to the pivot tile and to their own tile, factor the
-//     pivot tile (redundantly, reciprocal square roots) and solve X = C Ld^-T: final tiles of L.
-//   * 136 threads (warps 1,2,3,5,6) each keep one 4 x 4 tile (ti, tk), ti >= tk, of the trailing block in registers, apply the
-//     update of column s-1 and publish column s+1 for the next step.
+// The sweep is bound by ONE warp: the one that carries the pivot chain (cycle probes: a lone warp issues a DFMA every
+// 2.1 cycles, a dependent one every 8.3, the reciprocal square root takes 49; that warp ends up limited by the issue
+// of its ~260 instructions per step, not by the chain alone), so the design keeps that warp's instruction stream
+// minimal and divergence-free, keeps its scheduler free of other busy warps and gives every other job to other
+// warps.  384 threads in 12 warps:
+//   * warp 0: the owners of tile column s (4 pivots), two lanes per tile (two rows each).  They read the column as
+//     published one step earlier, apply the pending rank-4 update of column s-1 to the pivot tile and to their own
+//     tile, factor the pivot tile (redundantly, reciprocal square roots) and solve X = C Ld^-T: final tiles of L.
+//   * 136 threads (warps 1,2,3,5,6) each keep one 4 x 4 tile (ti, tk), ti >= tk, of the trailing block in
+//     registers, apply the update of column s-1 and publish column s+1 for the next step.
 //   * 120 threads (warps 7,9,10,11) each build one off-diagonal 4 x 4 tile (i, c) of X = L^-1,
 //     X[i][c] = -Xd_i sum_{k=c}^{i-1} L[i][k] X[k][c], one tile product per step as its operands become final.
-//   * one thread of warp 4 turns the pivot-tile numbers of the previous step into the diagonal tiles of L and X and checks
-//     the pivots.
+//   * one thread of warp 4 turns the pivot-tile numbers of the previous step into the diagonal tiles of L and X and
+//     checks the pivots; warp 8 is idle (warps 4 and 8 sit on warp 0's scheduler).
+// Measured and dropped: letting the other warps wait for warp 0's shared-memory loads (named barrier), moving the
+// solve to a second warp fed through shared memory (+14 % sweep time: the hand-off costs more than the overlap of
+// solve and pivot chain it gives up), issuing the four reciprocal square roots together.
 // One barrier per step, 18 steps; final tiles live in shared memory (packed 4 x 4, 18-double stride: conflict-free
 // 128-bit accesses) and all global writes (factor, 64 x 64 inverse block for the panel product, mirrored copy in
 // the triangular-inverse buffer) happen once at the end, by all threads.
