@@ -18,6 +18,9 @@
  *   - random variates are INPUTS (the R host draws them in the reference's order), so results are
  *     reproducible against the reference with the same variates.
  *   - there is no CPU fallback: every function needs a CUDA device and fails with SPW_ERR_CUDA.
+ *   - threading: R calls from one thread and so should other hosts.  Each device has ONE context (stream,
+ *     workspaces, plans): calls that use the same device must not overlap; calls on different devices may
+ *     (spw_gradient_run itself drives its ngpu devices from internal threads that join before it returns).
  */
 #ifndef SPWOMBLING_H
 #define SPWOMBLING_H
