@@ -527,9 +527,9 @@ trmv_lower_kernel(int n, MatView T, const double* __restrict__ x, long long ldx,
 }
 
 // sum log diag(L) and ||row n||^2 (deterministic single-CTA reduction per batch entry)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 logdet_quad_kernel(int n, MatView L, double* __restrict__ logdet_half, double* __restrict__ quad) {
-  __shared__ double red[2][8];
+  __shared__ double red[2][32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const double* Lp = L.p + (long long)b * L.stride;
   double sl = 0.0, sq = 0.0;
@@ -549,7 +549,7 @@ logdet_quad_kernel(int n, MatView L, double* __restrict__ logdet_half, double* _
   __syncthreads();
   if (tid == 0) {
     double a = 0.0, c = 0.0;
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
       a += red[0][w];
       c += red[1][w];
     }
@@ -999,7 +999,8 @@ int trmv_lower_batched(int n, MatView T, const double* x, long long ldx, double*
 
 int logdet_quad_batched(int n, MatView L, double* logdet_half, double* quad, int batch, cudaStream_t st) {
   if (batch <= 0) return SPW_OK;
-  logdet_quad_kernel<<<batch, 256, 0, st>>>(n, L, logdet_half, quad);
+  // the diagonal is a strided, latency-bound read: one matrix gets a full-size CTA, batches fill the SMs anyway
+  logdet_quad_kernel<<<batch, batch == 1 ? 1024 : 256, 0, st>>>(n, L, logdet_half, quad);
   SPW_LAUNCHED();
   return SPW_OK;
 }
