@@ -4,11 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # one process per GPU (torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the restated reference algorithm on host cores
 
-A "step" is one pass of the hot path over one batch of synthetic posterior samples (per rank; weak scaling):
-covariance assembly -> batched Cholesky -> triangular inverse -> cross-covariances -> fused TRMM + Gram +
-5x5 Cholesky + draw for every grid point, plus (N > 1) the single NCCL gather of the draws to rank 0.
-`value` is measured with inputs resident in HBM; `e2e` goes through the public multi-rank entry point with
-pinned HOST inputs (H2D inside the timed region) and reads the summary and the draws back to the host.
+A "step" is one pass of the hot path over a FIXED batch of synthetic posterior samples (strong scaling: the
+same S_total samples per step at every N, split into contiguous shards over the ranks as the reference's mclapply
+does): covariance assembly -> batched Cholesky -> triangular inverse -> cross-covariances -> fused TRMM + Gram +
+5x5 Cholesky + draw for every grid point, then the single NCCL gather of the draws to rank 0 and the batch-median /
+HPD summary there (both inside the timed region).
+`value` is measured with inputs resident in HBM (one process per GPU, torch.distributed NCCL gather); `e2e` is the
+same step through the C ABI R binds -- `spw_gradient_run` with HOST buffers and `ngpu = N` driven from rank 0
+(in-process sharding, grouped NCCL send/recv gather, summary, draws and estimates copied back to the host).
+Rank 0 also recomputes one gathered sample alone and requires bit-identical draws (`parity_checked`).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -31,18 +35,18 @@ UNIT = "sample*gridpoint/s"
 WORKLOADS = {
     # BASELINE.json configs[4] (the configuration the metric's 2/4/8-GPU figures are quoted on; it fits one GPU)
     "c5": dict(name="C5: synthetic N=5000 uniform coords, matern2, 100x100 grid", n=5000, cov="matern2", gside=100,
-               phi=(100.0, 200.0), batch=8, g_cpu=16),
+               phi=(100.0, 200.0), samples=64, nbatch=8, g_cpu=16),
     # BASELINE.json configs[3]
     "c4": dict(name="C4: synthetic N=2000 uniform coords, gaussian, 60x60 grid", n=2000, cov="gaussian", gside=60,
-               phi=(3000.0, 6000.0), batch=64, g_cpu=32),
+               phi=(3000.0, 6000.0), samples=512, nbatch=8, g_cpu=32),
     # BASELINE.json configs[1] / configs[2] at their sizes (synthetic coordinates; the real datasets are test fixtures)
     "c2": dict(name="C2-size: N=155 (meuse), matern1, 50x50 grid", n=155, cov="matern1", gside=50,
-               phi=(2.0, 8.0), batch=1000, g_cpu=2500),
+               phi=(2.0, 8.0), samples=4000, nbatch=100, g_cpu=2500),
     "c3": dict(name="C3-size: N=506 (boston.c), matern2, 134 grid points (12x12 here)", n=506, cov="matern2", gside=12,
-               phi=(30.0, 60.0), batch=1000, g_cpu=144),
+               phi=(30.0, 60.0), samples=4000, nbatch=100, g_cpu=144),
     # BASELINE.json configs[0] (README synthetic)
     "c1": dict(name="C1: README synthetic N=100, matern2, 19x19 grid", n=100, cov="matern2", gside=19,
-               phi=(10.0, 30.0), batch=1000, g_cpu=361),
+               phi=(10.0, 30.0), samples=4000, nbatch=100, g_cpu=361),
 }
 
 
@@ -120,35 +124,56 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def config_of(w, world, S_total):
+    """The `config` object -- identical for our arm and the reference arm so that the driver compares like with like."""
+    G = w["gside"] ** 2
+    return {"workload": w["name"], "cov_type": w["cov"], "n": w["n"], "grid_points": G,
+            "samples_per_step": S_total, "units_per_step": S_total * G, "nbatch": w["nbatch"],
+            "flops_per_unit": flops_per_unit(w), "parallelism": "sample-sharded x%d" % world,
+            "l2": "inputs larger than L2: every step streams %.1f GB of factors and cross-covariances per %d samples "
+                  "(L2 is 126 MB); three distinct sample sets cycle" %
+                  ((2 * w["n"] ** 2 * 8 + ncomp(w["cov"]) * G * w["n"] * 8) * min(S_total, 8) / 1e9, min(S_total, 8))}
+
+
+def cpu_baseline_leg(w, workers=None):
+    """Bounded CPU sample of the workload: `workers` forked single-threaded workers (the reference's mclapply shape,
+    R/spatial_gradient.R:29-32), one posterior sample each, g_cpu grid points, extrapolated to the whole grid."""
+    from oracle import baseline
+    cores = os.cpu_count() or 1
+    workers = max(1, cores - 1) if workers is None else workers      # detectCores() - 1
+    coords, grid, phi, sig2, z, eps = make_inputs(w, workers)         # one sample per worker, whatever the core count
+    G = grid.shape[0]
+    g_cpu = min(w["g_cpu"], G)
+    r = baseline.gradient_reference_step(coords, grid, w["cov"], phi, sig2, z, eps, g_cpu, workers)
+    r["sample"] = ("%d forked workers x 1 BLAS thread (the reference's mclapply shape), 1 sample each, %d of %d grid "
+                   "points, extrapolated per worker as G/(t_factor + G*t_grid) with t_factor=%.2fs, t_grid=%.4fs, summed "
+                   "over workers; restated reference algorithm (NumPy+OpenBLAS), not R"
+                   % (workers, g_cpu, G, r["t_factor"], r["t_grid"]))
+    r["workers"] = workers
+    r["host"] = baseline.host_info()
+    return r
+
+
 # ---- reference arm: the restated reference algorithm on the host cores --------------------------------------
 def run_reference(args, w):
-    from oracle import baseline
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    workers = max(1, cores - 1)                       # R/spatial_gradient.R:29-30: detectCores() - 1
-    coords, grid, phi, sig2, z, eps = make_inputs(w, workers)
-    G = grid.shape[0]
-    g_cpu = min(w["g_cpu"], G)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    S_total = args.samples or w["samples"]
     vals, walls = [], []
     for it in range(args.warmup + args.steps):
-        r = baseline.gradient_reference_step(coords, grid, w["cov"], phi, sig2, z, eps, g_cpu, workers)
+        r = cpu_baseline_leg(w)
         if it >= args.warmup:
             vals.append(r["units_per_s"])
             walls.append(r["wall"])
-            last = r
     value = float(np.median(vals))
-    sample = ("%d forked workers x 1 BLAS thread, 1 sample each, %d of %d grid points; per worker rate = "
-              "G/(t_factor + G*t_grid), t_factor=%.2fs t_grid=%.4fs (mean), summed over workers; restated reference "
-              "algorithm (NumPy+OpenBLAS), not R" % (workers, g_cpu, G, last["t_factor"], last["t_grid"]))
-    hi = baseline.host_info()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls)) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "cov_type": w["cov"], "n": w["n"], "grid_points": G},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
-                             "host": hi},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(w, world, S_total),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["workers"], "kind": "port", "sample": r["sample"],
+                             "host": r["host"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -172,42 +197,53 @@ def run_ours(args, w):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        # host-side rendezvous for the e2e leg: ranks > 0 must not spin in an NCCL barrier kernel on the GPUs that
+        # rank 0's in-process spw_gradient_run(ngpu = N) is using
+        cpu_group = dist.new_group(backend="gloo")
     lib = spw.load()
     lib.spw_set_device(local)
     n, cov, c = w["n"], w["cov"], ncomp(w["cov"])
-    B = args.batch or w["batch"]
-    npool = 3                                            # distinct sample batches cycled through the steps
-    coords, grid, phi, sig2, z, eps = make_inputs(w, B * npool, seed0=1000 * rank)
+    S_total = args.samples or w["samples"]
+    nbatch_sum = min(w["nbatch"], max(1, S_total // 2))
+    lo, hi = dev.shard_bounds(S_total, world, rank)
+    npool = 3                                            # distinct sample sets cycled through the steps
+    pools = [make_inputs(w, S_total, seed0=1000 * i) for i in range(npool)]
+    coords, grid = pools[0][0], pools[0][1]
     G = grid.shape[0]
     coords_d = dev.coords_to_device(coords, device)
     grid_d = dev.coords_to_device(grid, device)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
-    host = [dict(phi=pin(phi[i * B:(i + 1) * B]), sig2=pin(sig2[i * B:(i + 1) * B]), z=pin(z[i * B:(i + 1) * B]),
-                 eps=pin(eps[i * B:(i + 1) * B])) for i in range(npool)]
-    devb = [{k: v.to(device) for k, v in h.items()} for h in host]
-    draws_buf = torch.empty((B, c, G), dtype=torch.float64, device=device)
-    nbatch_sum = 2
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(device)   # noqa: E731
+    devb = [dict(phi=up(p[2]), sig2=up(p[3]), z=up(p[4]), eps=up(p[5])) for p in pools]
+    draws_buf = torch.empty((hi - lo, c, G), dtype=torch.float64, device=device)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def barrier_host():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     def step_resident(i):
+        # one process per GPU: this rank's contiguous shard, ONE gather to rank 0, summary on rank 0
         d = devb[i % npool]
         mine = dev.gradient_shard(coords_d, grid_d, cov, d["phi"], d["sig2"], d["z"], d["eps"], out=draws_buf)
-        if world > 1:
-            return dev.gather_shards(mine, B * world)
-        return mine
+        full = dev.gather_shards(mine, S_total) if world > 1 else mine
+        if rank == 0:
+            return full, dev.hpd_summary_dev(full, nbatch_sum)
+        return None, None
 
     def step_e2e(i):
-        # the public multi-rank entry point: pinned host shard in, the reference's list (estimates + draws) out on rank 0
-        h = dict(host[i % npool])
-        h["S_total"] = B * world
-        return dev.spatial_gradient_sharded(coords, None, cov, grid, nbatch=nbatch_sum, return_mcmc=True, local=h,
-                                            device=device, rounded=False)
+        # the C ABI R binds (spw_gradient_run): host buffers in, estimates + draws out, ngpu = N driven from rank 0
+        if rank != 0:
+            return None
+        p = pools[i % npool]
+        return spw.spatial_gradient(coords, {"phi": p[2], "sig2": p[3], "z": p[4]}, cov, grid, nbatch=nbatch_sum,
+                                    return_mcmc=True, eps=p[5], ngpu=world, rounded=False)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, barrier=barrier):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -222,7 +258,7 @@ def run_ours(args, w):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    units_per_step = B * G * world
+    units_per_step = S_total * G
     # ---- value: HBM-resident inputs, phase events and clocks sampled during the timed region ----
     for i in range(args.warmup):
         step_resident(i)
@@ -243,22 +279,45 @@ def run_ours(args, w):
     lib.spw_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     value = units_per_step * args.steps / (ms_total * 1e-3)
-    # ---- e2e: pinned host inputs -> H2D -> shard -> gather -> summary + draws -> D2H ----
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    # ---- multi-GPU parity, visible to the driver: the last sample of the gathered block (it lives on the last rank)
+    #      recomputed alone on rank 0 must be bit-identical (sharding and batching change no arithmetic) ----
+    last_i = args.warmup + args.steps - 1
+    full, summ_dev = step_resident(last_i)
+    parity = None
+    if rank == 0:
+        p = pools[last_i % npool]
+        one = lambda a: torch.from_numpy(np.ascontiguousarray(a[S_total - 1:S_total])).to(device)   # noqa: E731
+        alone = dev.gradient_shard(coords_d, grid_d, cov, one(p[2]), one(p[3]), one(p[4]), one(p[5]))
+        parity = bool(torch.equal(alone[0], full[S_total - 1]))
+        summ_value_leg = summ_dev.cpu().numpy()
+        draws_value_leg = full[S_total - 1].cpu().numpy()
+    barrier()
+    # ---- e2e: host buffers -> spw_gradient_run(ngpu = N) -> estimates + draws on the host ----
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), barrier_host)
     e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(int(v.numel()) * 8 for v in host[0].values()) + (coords.size + grid.size) * 8
-    d2h = (c * 3 * G + B * world * c * G) * 8
+    h2d = (S_total * (2 + n + G * c) + coords.size + grid.size) * 8
+    d2h = (c * 3 * G + S_total * c * G) * 8
+    out_e2e = step_e2e(last_i)
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
+    # the C-ABI path (in-process sharding, its own gather) against the torch.distributed path: same bytes
+    names = ("s1", "s2", "s11", "s12", "s22")[:c]
+    est_names = ("grad1.est", "grad2.est", "grad11.est", "grad12.est", "grad22.est")[:c]
+    e2e_draws = np.stack([np.asarray(out_e2e["grad.%s.mcmc" % nm])[S_total - 1] for nm in names])
+    e2e_summ = np.stack([np.asarray(out_e2e[k]).T for k in est_names])
+    parity_e2e = bool(np.array_equal(e2e_draws, draws_value_leg) and np.array_equal(e2e_summ, summ_value_leg))
+    if not (parity and parity_e2e):
+        raise SystemExit("bench.py: multi-GPU parity check failed (gathered sample vs single-rank recompute: %s; "
+                         "spw_gradient_run vs torch.distributed path: %s)" % (parity, parity_e2e))
     # ---- roofline of the dominant kernel (fused TRMM + Gram + draw) ----
     peaks = {}
     for f in ("profiles/FP64_PEAK.json", "MEASURED_PEAKS.json"):
-        p = os.path.join(ROOT, f)
-        if os.path.exists(p):
-            peaks.update(json.load(open(p)))
+        pth = os.path.join(ROOT, f)
+        if os.path.exists(pth):
+            peaks.update(json.load(open(pth)))
     peak_tf = float(peaks.get("fp64_tensor_tflops", 37.0))
     main_ms, main_calls = ph_ms[5], max(1, ph_calls[5])
     achieved_tf = main_flops.value / (main_ms * 1e-3) / 1e12 if main_ms > 0 else None
@@ -266,42 +325,36 @@ def run_ours(args, w):
     tp = os.path.join(ROOT, "profiles", "main_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload)
-    names = ["cov_assemble", "potrf", "trtri", "trmv", "cross_cov", "gradient_main"]
-    phases = {nm: {"ms_per_step": ph_ms[i] / args.steps, "launch_groups": int(ph_calls[i])} for i, nm in enumerate(names)}
+    names_ph = ["cov_assemble", "potrf", "trtri", "trmv", "cross_cov", "gradient_main"]
+    phases = {nm: {"ms_per_step": ph_ms[i] / args.steps, "launch_groups": int(ph_calls[i])} for i, nm in enumerate(names_ph)}
     roofline = {"bound": "tensor", "kernel": "gradient_tma_kernel (TMA-fed fused TRMM + Gram + 5x5 chol + draw)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                 "peak_source": "measured FP64 tensor pipe (DMMA.8x8x4 micro-benchmark, profiles/FP64_PEAK.json; "
                                "MEASURED_PEAKS.json has no FP64 entry)",
                 "ms_per_launch": main_ms / main_calls, "flops_per_launch": main_flops.value / main_calls,
-                "share_of_step": main_ms / ms_total}
+                "share_of_step": main_ms / ms_total,
+                "note": "rank 0's launches; traffic is per launch of 8 samples (ncu --set full, profiles/)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "cov_type": cov, "n": n, "grid_points": G,
-                       "samples_per_rank_per_step": B, "units_per_step": units_per_step,
-                       "flops_per_unit": flops_per_unit(w), "parallelism": "sample-sharded x%d" % world,
-                       "l2": "inputs larger than L2: per step the kernels stream %.1f GB of factors and "
-                             "cross-covariances (L2 is 126 MB); sample batches cycle" %
-                             ((2 * n * n * 8 + c * G * n * 8) * B / 1e9)},
+            "config": config_of(w, world, S_total),
             "algorithmic_tflops": value * flops_per_unit(w) / 1e12,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": "spw_gradient_run (C ABI, host buffers, ngpu=%d in-process from rank 0%s)" %
+                            (world, ", gather via NCCL" if lib.spw_last_gather_used_nccl() == 1 else
+                             (", gather via peer copies" if world > 1 else ""))},
+            "parity_checked": True,
+            "parity": {"gathered_sample_vs_single_rank_recompute": "bit-identical",
+                       "c_abi_path_vs_torch_distributed_path": "bit-identical (draws of the last sample and all estimates)"},
             "gpu_launches": int(launches), "roofline": roofline, "phases": phases}
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     if world == 1 and not args.no_cpu:
-        from oracle import baseline
-        cores = os.cpu_count() or 1
-        workers = max(1, cores - 1)
-        g_cpu = min(w["g_cpu"], G)
-        r = baseline.gradient_reference_step(coords, grid, cov, phi, sig2, z, eps, g_cpu, workers)
-        line["cpu_baseline"] = {"value": r["units_per_s"], "unit": UNIT, "cores": workers, "kind": "port",
-                                "sample": "%d forked workers x 1 BLAS thread (the reference's mclapply shape), 1 sample "
-                                          "each, %d of %d grid points, extrapolated per worker as G/(t_factor + G*t_grid) "
-                                          "with t_factor=%.2fs, t_grid=%.4fs; restated reference algorithm "
-                                          "(NumPy+OpenBLAS), not R" % (workers, g_cpu, G, r["t_factor"], r["t_grid"]),
-                                "host": baseline.host_info()}
+        r = cpu_baseline_leg(w)
+        line["cpu_baseline"] = {"value": r["units_per_s"], "unit": UNIT, "cores": r["workers"], "kind": "port",
+                                "sample": r["sample"], "host": r["host"]}
     # ---- secondary metric: hlmBayes_sp MCMC iterations / s at 1 GPU ----
     if world == 1 and not args.no_hlm:
         line["hlm"] = bench_hlm(spw, args)
@@ -382,7 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="posterior samples per rank per step")
+    ap.add_argument("--samples", type=int, default=0, help="posterior samples per step (whole job, split over the ranks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-hlm", action="store_true", help="skip the hlmBayes_sp secondary metric")
     args = ap.parse_args()

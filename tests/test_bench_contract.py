@@ -29,3 +29,22 @@ def test_non_root_rank_of_reference_arm_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
                         "--steps", "1", "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_leg_runs_for_any_core_count(monkeypatch):
+    """Round 1's N=1 scaling arm died because the CPU leg indexed 24 samples with cores - 1 = 31 workers: the leg
+    now draws exactly one sample per worker, whatever the core count."""
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(os, "cpu_count", lambda: 64)
+    r = bench.cpu_baseline_leg(bench.WORKLOADS["c1"])
+    assert r["workers"] == 63 and r["units_per_s"] > 0 and "63 forked workers" in r["sample"]
+
+
+def test_both_arms_share_one_config_object():
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["c5"]
+    cfg = bench.config_of(w, 1, w["samples"])
+    assert cfg["workload"].startswith("C5") and cfg["units_per_step"] == w["samples"] * 10000
+    assert "model" not in cfg
