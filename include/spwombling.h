@@ -63,6 +63,10 @@ int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset
 
 /* diagnostic: first call enables cycle counters in the diagonal-block kernel, later calls read 16 of them */
 int spw_debug_diag_timing(long long* out16);
+/* diagnostic (SPW_DAG_TRACE=1): per-task trace of the last persistent single-matrix Cholesky of order n (+ extra
+ * appended rows) on the current device; 4 words per task (packed id, start ns, end ns, 2 * SM + sub-worker).
+ * Returns the number of words written (<= cap_words). */
+long long spw_debug_dag_trace(int n, int extra, unsigned long long* out, long long cap_words);
 
 /* covariance kernels ----------------------------------------------------------------------------
  * spw_cov: as.matrix(dist(coords)) fused with cov_gaussian / cov_matern1 / cov_matern2

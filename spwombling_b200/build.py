@@ -10,7 +10,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libspwombling.so")
-SOURCES = ["api.cu", "cov.cu", "linalg.cu", "gradient.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
+SOURCES = ["api.cu", "cov.cu", "linalg.cu", "potrf_dag.cu", "gradient.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
 # cov.cu is compiled without FMA contraction: its elementwise formulas then round exactly like the reference's
 # R arithmetic (and K[i][j] == K[j][i] bit for bit, whichever thread computes it)
 EXTRA_FLAGS = {"cov.cu": ["-fmad=false"]}
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s: %s" % (src, " ".join(cmd)))
-    if rebuilt or not os.path.exists(LIB):
+    if rebuilt or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB

@@ -18,6 +18,7 @@
 #include "gradient.cuh"
 #include "hlm.cuh"
 #include "linalg.cuh"
+#include "potrf_dag.cuh"
 #include "summary.cuh"
 
 namespace spw {
@@ -92,6 +93,7 @@ struct PhaseTimer {
 struct DeviceCtx {
   cudaStream_t stream = nullptr;
   std::map<std::tuple<int, int, int>, LinalgPlan*> plans;
+  std::map<std::pair<int, int>, DagPlan*> dag_plans;
   void* ws = nullptr;          // grow-only workspace
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
@@ -155,6 +157,31 @@ static int get_plan(DeviceCtx& c, int n, int extra, int single, const LinalgPlan
       return rc;
     }
     it = c.plans.emplace(key, p).first;
+  }
+  *out = it->second;
+  return SPW_OK;
+}
+
+// Persistent tile-DAG Cholesky plan for one matrix of order n (nullptr: use the multi-launch schedule).
+// SPW_DAG=0 disables it, SPW_DAG_MIN sets the smallest order it is used for.
+static int get_dag_plan(DeviceCtx& c, int n, int extra, const DagPlan** out) {
+  *out = nullptr;
+  const char* env = getenv("SPW_DAG");
+  if (!(env && env[0] == '1')) return SPW_OK;      // work in progress: opt-in
+  const char* env_min = getenv("SPW_DAG_MIN");
+  const int nmin = env_min ? atoi(env_min) : 256;
+  if (n < nmin) return SPW_OK;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto key = std::make_pair(n, extra);
+  auto it = c.dag_plans.find(key);
+  if (it == c.dag_plans.end()) {
+    DagPlan* p = new DagPlan();
+    int rc = dag_plan_build(*p, n, extra);
+    if (rc != SPW_OK) {
+      delete p;
+      return rc;
+    }
+    it = c.dag_plans.emplace(key, p).first;
   }
   *out = it->second;
   return SPW_OK;
@@ -566,19 +593,40 @@ int spw_debug_diag_timing(long long* out16) {
   return SPW_OK;
 }
 
+// diagnostic (SPW_DAG_TRACE=1): per-task trace of the last persistent-Cholesky run of order n (extra appended rows) on the
+// current device: 4 words per task (packed id, start ns, end ns, 2 * SM + sub-worker).  Returns the words written.
+long long spw_debug_dag_trace(int n, int extra, unsigned long long* out, long long cap_words) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  DeviceCtx& c = g_ctx[dev & 63];
+  auto it = c.dag_plans.find(std::make_pair(n, extra));
+  if (it == c.dag_plans.end()) return 0;
+  cudaDeviceSynchronize();
+  std::vector<unsigned long long> v;
+  if (dag_trace_read(*it->second, v) != SPW_OK) return -1;
+  const long long cnt = std::min<long long>((long long)v.size(), cap_words);
+  if (out && cnt > 0) memcpy(out, v.data(), sizeof(unsigned long long) * cnt);
+  return cnt;
+}
+
 int spw_shutdown(void) {
   int cur = 0, ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess) return SPW_OK;
   cudaGetDevice(&cur);
   for (int d = 0; d < ndev && d < 64; ++d) {
     DeviceCtx& c = g_ctx[d];
-    if (!c.stream && !c.ws && c.plans.empty()) continue;
+    if (!c.stream && !c.ws && c.plans.empty() && c.dag_plans.empty()) continue;
     cudaSetDevice(d);
     for (auto& kv : c.plans) {
       plan_free(*kv.second);
       delete kv.second;
     }
     c.plans.clear();
+    for (auto& kv : c.dag_plans) {
+      dag_plan_free(*kv.second);
+      delete kv.second;
+    }
+    c.dag_plans.clear();
     if (c.ws) cudaFree(c.ws);
     c.ws = nullptr;
     c.ws_bytes = 0;
@@ -684,9 +732,15 @@ int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) 
   SPW_CUDA(cudaMemcpy2DAsync(dm.p, sizeof(double) * ld, a, sizeof(double) * n, sizeof(double) * n, n,
                              cudaMemcpyHostToDevice, st));
   MatView L{dm.as<double>(), ld, (long long)n * ld};
-  Lookahead* la;
-  SPW_TRY(get_lookahead(*ctx, n, &la));
-  SPW_TRY(potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st, la));
+  const DagPlan* dag;
+  SPW_TRY(get_dag_plan(*ctx, n, 0, &dag));
+  if (dag) {
+    SPW_TRY(potrf_dag(*dag, L, dd.as<double>(), ds.as<int>(), st));
+  } else {
+    Lookahead* la;
+    SPW_TRY(get_lookahead(*ctx, n, &la));
+    SPW_TRY(potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st, la));
+  }
   SPW_TRY(logdet_quad_batched(n, L, dl.as<double>(), nullptr, 1, st));
   std::vector<double> tmp((size_t)n * n);
   int status = 0;
@@ -756,6 +810,7 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   ws.state = (HlmState*)dstate.p;
   ws.plan = plan;
   SPW_TRY(get_lookahead(*ctx, n, &ws.la));
+  SPW_TRY(get_dag_plan(*ctx, n, 1, &ws.dag));
   int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
                        b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
                        o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);

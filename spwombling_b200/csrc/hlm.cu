@@ -411,7 +411,8 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
     // Sigma' (lower triangle) from the proposed parameters held in device memory
     SPW_TRY(cov_assemble_batched(type, n, cx, cy, &S->prop[2], &S->prop[0], &S->prop[1], 0, L, 1, 1, st));
     SPW_CUDA(cudaMemcpyAsync(ws.L + (long long)n * ws.ld, y_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    SPW_TRY(potrf_batched(*ws.plan, L, ws.dinv, nullptr, 1, ws.status, st, ws.la));
+    if (ws.dag) SPW_TRY(potrf_dag(*ws.dag, L, ws.dinv, ws.status, st));
+    else SPW_TRY(potrf_batched(*ws.plan, L, ws.dinv, nullptr, 1, ws.status, st, ws.la));
     SPW_TRY(logdet_quad_batched(n, L, &S->logdet_p, &S->quad_p, 1, st));
     hlm_accept_kernel<<<1, 1, 0, st>>>(S, c, p, unif_dev, ho);
     SPW_LAUNCHED();

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
+#include "potrf_dag.cuh"
 
 namespace spw {
 
@@ -15,6 +16,7 @@ struct HlmWorkspace {
   HlmState* state = nullptr;
   const LinalgPlan* plan = nullptr;   // built with extra_rows = 1
   Lookahead* la = nullptr;            // optional lookahead schedule of the Cholesky
+  const DagPlan* dag = nullptr;       // persistent tile-DAG Cholesky (one kernel per factorisation); overrides plan / la
 };
 
 size_t hlm_state_bytes();

@@ -1,0 +1,831 @@
+// Single-matrix blocked Cholesky as ONE persistent cooperative kernel (sm_100a, fp64).
+//
+// Why: the chain of hlmBayes_sp (R/hlmBayes_sp.R:114,140,181) factors one matrix of order N+1 per proposal, strictly
+// one after the other.  As a sequence of launches the factorisation is bound by its critical path (79 diagonal
+// blocks, each followed by a panel product and an update before the next diagonal block can start) and by the
+// stream edges between ~400 small kernels.  Here the dependencies live in global-memory flags instead:
+//
+//   * CTA 0 ("chain") factors and inverts the 64 x 64 diagonal blocks one after the other (the warp-role sweep of
+//     diag_factor.cuh) and publishes each block with a release store;
+//   * every other CTA holds two independent 8-warp "sub-workers" (the 128 x 64 TMA-fed DMMA tile engine of
+//     linalg.cu; two per SM so that one hides the C read-modify-write of the other).  A sub-worker never blocks:
+//     its first warp keeps up to one claimed *urgent* task (panel products and K = 64 updates, queued per source
+//     column and released when the chain has published that column) and one claimed *bulk* task (K = 256 trailing
+//     updates, one global queue), polls their flags, and runs whichever becomes ready -- urgent first;
+//   * flags: upd[row block][column block] counts the source columns already applied to that 64 x 64 block; the
+//     panel product of column c needs upd == c and leaves c + 1 ("final").  An update waits for its operand blocks
+//     to be final and for the previous update of its own block.
+//
+// Both queues are in topological order and claims are made in order, so the earliest unfinished task is always
+// either running, held by a worker that polls it, or claimable by a worker with a free slot: no deadlock as long
+// as all CTAs are resident, which the cooperative launch guarantees.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "potrf_dag.cuh"
+#include "tma.cuh"
+#include "diag_factor.cuh"
+
+namespace spw {
+
+namespace {
+constexpr int D_BK = 32, D_LDS = D_BK + 4, D_BM = 128, D_BN = 64, D_STAGES = 2;
+constexpr int D_SUB = 256;                 // threads of a sub-worker (8 warps)
+constexpr int D_THREADS = 2 * D_SUB;       // two sub-workers per CTA; the chain CTA uses 12 of its 16 warps
+constexpr int D_A_STAGE = D_BM * D_LDS, D_B_STAGE = D_BN * D_LDS, D_STAGE = D_A_STAGE + D_B_STAGE;   // doubles
+constexpr uint32_t D_STAGE_BYTES = D_STAGE * sizeof(double);
+constexpr size_t D_SUB_SMEM = size_t(D_STAGES) * D_STAGE_BYTES;
+constexpr size_t D_SMEM = 2 * D_SUB_SMEM + 256;
+constexpr int OUTER = OUTER_W / NB;        // source columns per bulk update (4)
+static_assert(sizeof(DiagSmem) <= 2 * D_SUB_SMEM, "chain CTA state must fit in the worker ring");
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes of other SMs are read here through the async proxy (TMA) and vice versa
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void sub_barrier(int sw) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(1 + sw), "n"(D_SUB) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(v));
+  return v;
+}
+}  // namespace
+
+struct DagParams {
+  const DagTask* utasks;
+  const int* useg;
+  const DagTask* btasks;   // bulk tasks, one queue per source outer block: queue m = [bseg[m], bseg[m+1]), by target column
+  const int* bseg;
+  int nq;
+  int* upd;        // [nrb][nblk]
+  int* uhead;      // [nblk]
+  int* bhead;      // [nq]
+  int* chain_pos;  // 1
+  int* active;     // 1: row tasks being executed
+  int active_cap;
+  MatView L;
+  double* dinv;
+  int n, rows, nblk, nrb;
+  int* status;
+  unsigned long long* trace;
+  int trace_cap;
+  int* trace_ctr;
+};
+
+__device__ __forceinline__ int dag_rstart(int b, int n, int rows, int nblk) {
+  return b <= nblk ? min(b * NB, n) : rows;
+}
+
+// Flag word of a 64 x 64 block: the number of source columns applied to it so far (in any order: the updates of a
+// block commute), c + 1 once the panel product of column c has made it final, and a lock bit that an update holds
+// only while its epilogue reads, modifies and writes the block.
+constexpr int FLAG_LOCK = 1 << 30;
+
+// One polling round over the flags a task depends on (warp-collective; every lane reads at most one flag).
+//   panel product of column c: the diagonal block is published; every source column < c has been applied to its blocks
+//   update: its operand blocks are final (the block itself is locked in the epilogue, not here)
+__device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, int nblk, int lane) {
+  int b = -1, c = 0, want = 0;
+  if (t.type == 0) {
+    if (lane == 0) { b = t.cb; c = t.cb; want = t.cb + 1; }
+    else if (lane <= t.nrb) { b = t.rb + lane - 1; c = t.cb; want = t.cb; }
+  } else {
+    const int nk = t.k1 - t.k0, na = t.nrb * nk;
+    if (lane < na) { b = t.rb + lane / nk; c = t.k0 + lane % nk; want = c + 1; }
+    else if (lane < na + nk) { b = t.cb; c = t.k0 + (lane - na); want = c + 1; }
+  }
+  bool ok = true;
+  if (b >= 0) ok = (ld_acquire(upd + b * nblk + c) == want);
+  return __all_sync(0xffffffffu, ok);
+}
+
+// ---- the tile engine: C[128 x 64] (+)= alpha * A[128 x K] * B[64 x K]^T, operands by TMA, 8 warps (4 x 2) ----
+// NARROW (one row block, m <= 64): the 8 warps are laid out 2 x 4 (warp tile 32 x 16) so that all four tensor pipes
+// work on the 64 x 64 tile -- these are the tasks next to the band of the chain CTA, whose latency the chain sees.
+template <bool NARROW>
+__device__ __forceinline__ void dag_execute(const DagTask& t, const DagParams& P, const CUtensorMap* tmA,
+                                            const CUtensorMap* tmB, const CUtensorMap* tmD, double* pipe,
+                                            unsigned long long* full, unsigned long long* empty, unsigned& kbase,
+                                            int sw, int wtid) {
+  const int lane = wtid & 31, warp = wtid >> 5;
+  const int row0 = dag_rstart(t.rb, P.n, P.rows, P.nblk);
+  const int m = dag_rstart(t.rb + t.nrb, P.n, P.rows, P.nblk) - row0;
+  const int c0 = t.cb * NB, ncol = min(NB, P.n - c0);
+  const bool panel = (t.type == 0);
+  const int a_col = panel ? c0 : t.k0 * NB;
+  const int K = panel ? ncol : (t.k1 - t.k0) * NB;
+  const int nkt = (K + D_BK - 1) / D_BK;
+  const int b_row = c0, b_col = panel ? 0 : t.k0 * NB;
+  const CUtensorMap* tb = panel ? tmD : tmB;
+  fence_proxy_async();
+  auto issue = [&](int kt) {
+    const unsigned f = kbase + kt;
+    const int s = f % D_STAGES;
+    mbar_wait(&empty[s], ((f / D_STAGES) & 1) ^ 1);
+    double* st = pipe + (size_t)s * D_STAGE;
+    mbar_expect_tx(&full[s], D_STAGE_BYTES);
+    tma_load_3d(st, tmA, a_col + kt * D_BK, row0, 0, &full[s]);
+    tma_load_3d(st + D_A_STAGE, tb, b_col + kt * D_BK, b_row, 0, &full[s]);
+  };
+  if (wtid == 0) {
+    for (int kt = 0; kt < D_STAGES - 1 && kt < nkt; ++kt) issue(kt);
+  }
+  constexpr int MF = 4, NF = NARROW ? 2 : 4, WN = 8 * NF;
+  const int warp_m = NARROW ? (warp & 1) : (warp & 3), warp_n = NARROW ? (warp >> 1) : (warp >> 2);
+  const int g = lane >> 2, q = lane & 3;
+  double acc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const bool live = warp_m * 32 < m;       // warps whose rows lie outside the tile only keep the ring moving
+  for (int kt = 0; kt < nkt; ++kt) {
+    const unsigned f = kbase + kt;
+    const int s = f % D_STAGES;
+    mbar_wait(&full[s], (f / D_STAGES) & 1);
+    if (lane == 0 && warp == (kt & 7) && kt + D_STAGES - 1 < nkt) issue(kt + D_STAGES - 1);
+    __syncwarp();
+    if (live) {
+      const double* As = pipe + (size_t)s * D_STAGE;
+      const double* a_base = As + (warp_m * 32 + g) * D_LDS + q;
+      const double* b_base = As + D_A_STAGE + (warp_n * WN + g) * D_LDS + q;
+#pragma unroll
+      for (int kk = 0; kk < D_BK / 4; ++kk) {
+        double a[MF], bf[NF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) a[i] = a_base[i * 8 * D_LDS + kk * 4];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) bf[j] = b_base[j * 8 * D_LDS + kk * 4];
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  kbase += nkt;
+  // ---- epilogue: panel: C = acc; update: C -= acc under the lock of its block(s) (lower row block first).  C may have
+  //      been written by another SM during this launch: read it past L1 (ld.global.cg) ----
+  int held[2] = {0, 0};
+  if (!panel) {
+    if (wtid == 0) {
+      for (int i = 0; i < t.nrb; ++i) {
+        int* f = P.upd + (t.rb + i) * P.nblk + t.cb;
+        for (;;) {
+          const int v = ld_acquire(f);
+          if (!(v & FLAG_LOCK) && atomicCAS(f, v, v | FLAG_LOCK) == v) { held[i] = v; break; }
+        }
+      }
+      __threadfence();
+    }
+    sub_barrier(sw);
+  }
+  double* Cp = P.L.p + (long long)row0 * P.L.ld + c0;
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      const int r = warp_m * 32 + i * 8 + g;
+      if (r >= m) continue;
+      double* crow = Cp + (long long)r * P.L.ld;
+      double2 old[NF];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = warp_n * WN + j * 8 + 2 * q;
+        old[j] = make_double2(0.0, 0.0);
+        if (!panel && c < ncol) {
+          if (c + 1 < ncol) old[j] = __ldcg(reinterpret_cast<const double2*>(crow + c));
+          else old[j].x = __ldcg(crow + c);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = warp_n * WN + j * 8 + 2 * q;
+        if (c >= ncol) continue;
+        const double v0 = panel ? acc[i][j][0] : old[j].x - acc[i][j][0];
+        const double v1 = panel ? acc[i][j][1] : old[j].y - acc[i][j][1];
+        if (c + 1 < ncol) __stcg(reinterpret_cast<double2*>(crow + c), make_double2(v0, v1));
+        else __stcg(crow + c, v0);
+      }
+    }
+  }
+  fence_proxy_async();
+  sub_barrier(sw);
+  if (wtid == 0) {
+    __threadfence();
+    for (int i = 0; i < t.nrb; ++i)
+      st_release(P.upd + (t.rb + i) * P.nblk + t.cb, panel ? t.cb + 1 : held[i] + (t.k1 - t.k0));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// The chain CTA in band mode: it owns the diagonal blocks AND the two row blocks below each of them.
+// Why: with diagonal blocks only, every step of the chain waits for two helper hops (panel product of tile
+// (j+1, j), then the update of (j+1, j+1)), each a flag round trip + claim + a small tile product at half an SM's
+// rate: 32 us per step measured against 15 us for the sweep itself.  Here the tiles within two blocks of the
+// diagonal never leave this SM between their last helper update and their final value:
+//   * while warps 0-11 run the sweep of block j, warps 12-15 ("background") fetch the three tiles of row block
+//     j+1 -- (j+1, j-1), (j+1, j), (j+1, j+1) -- as soon as the helpers have applied all sources k < j-1, finish
+//     L(j+1, j-1) = tile * Dinv_{j-1}^T, and apply source j-1 to the other two;
+//   * after the sweep all warps compute L(j+1, j) = tile * Dinv_j^T and S = A(j+1, j+1) - L(j+1, j) L(j+1, j)^T on
+//     the tensor pipe straight from shared memory (~2 us), and S is the input of the next sweep.
+// The helpers therefore have a whole step of slack for everything the chain consumes.
+// ---------------------------------------------------------------------------------------------------
+constexpr int C_LD = DIAG_SRC_LD;                 // 68: conflict-free DMMA fragment loads
+constexpr int C_TILE = NB * C_LD;
+struct ChainSmem {
+  DiagSmem diag;
+  double xprev[DIAG_LOW * DIAG_TS];   // packed inverse of the previous diagonal block
+  double bufS[C_TILE];                // tile (j+1, j+1): input of the next sweep
+  double bufX[2][C_TILE];             // tile (j+1, j) -> L(j+1, j); the other one holds L(j, j-1)
+  double bufT[C_TILE];                // tile (j+1, j-1) -> L(j+1, j-1)
+};
+static_assert(sizeof(ChainSmem) <= D_SMEM, "chain state must fit");
+
+template <int NT>
+__device__ __forceinline__ void chain_load_tile(double* __restrict__ dst, const double* __restrict__ src, long long ld,
+                                                int nr, int nc, int t) {
+  // all loads of a thread are issued before the first store: one L2 round trip per tile, not one per element
+  constexpr int PER = NB * (NB / 2) / NT;
+  double2 v[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = t + i * NT, r = e >> 5, c = (e & 31) * 2;
+    v[i] = make_double2(0.0, 0.0);
+    if (r < nr) {
+      if (c + 1 < nc) v[i] = __ldcg(reinterpret_cast<const double2*>(src + (long long)r * ld + c));
+      else if (c < nc) v[i].x = __ldcg(src + (long long)r * ld + c);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int e = t + i * NT, r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(dst + r * C_LD + c) = v[i];
+  }
+}
+
+// Dinv[8 nt + g][4 k4 + q] from the packed 4 x 4 tiles of the sweep (lower triangular: zero above the diagonal)
+__device__ __forceinline__ double chain_dinv_frag(const double* __restrict__ X, int nt, int k4, int g, int q) {
+  const int tr = 2 * nt + (g >> 2);
+  return (tr >= k4) ? X[diag_tile(tr, k4) * DIAG_TS + 4 * (g & 3) + q] : 0.0;
+}
+
+// rows 8 rg .. 8 rg + 7 of T * Dinv^T, written back in place and to global memory (bounded by nr x nc)
+__device__ __forceinline__ void chain_panel_rows(double* __restrict__ T, const double* __restrict__ X, int rg,
+                                                 double* __restrict__ gdst, long long ld, int nr, int nc, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  double acc[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  const double* arow = T + (8 * rg + g) * C_LD + q;
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const double a = arow[4 * k4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      if (nt >= (k4 >> 1)) dmma884(acc[nt][0], acc[nt][1], a, chain_dinv_frag(X, nt, k4, g, q));
+  }
+  __syncwarp();                      // every lane has read its part of the rows before they are overwritten
+  const int r = 8 * rg + g;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = 8 * nt + 2 * q;
+    *reinterpret_cast<double2*>(T + r * C_LD + c) = make_double2(acc[nt][0], acc[nt][1]);
+    if (r < nr) {
+      if (c + 1 < nc) __stcg(reinterpret_cast<double2*>(gdst + (long long)r * ld + c), make_double2(acc[nt][0], acc[nt][1]));
+      else if (c < nc) __stcg(gdst + (long long)r * ld + c, acc[nt][0]);
+    }
+  }
+}
+
+// rows 8 rg .. 8 rg + 7 of C -= A B^T (all 64 columns, K = 64)
+__device__ __forceinline__ void chain_update_rows(double* __restrict__ C, const double* __restrict__ A,
+                                                  const double* __restrict__ B, int rg, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  double acc[8][2];
+  double* crow = C + (8 * rg + g) * C_LD + 2 * q;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const double2 v = *reinterpret_cast<const double2*>(crow + 8 * nt);
+    acc[nt][0] = v.x; acc[nt][1] = v.y;
+  }
+  const double* arow = A + (8 * rg + g) * C_LD + q;
+  const double* brow = B + g * C_LD + q;
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const double a = -arow[4 * k4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], a, brow[8 * nt * C_LD + 4 * k4]);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(crow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+}
+
+// 8 x 8 tile t (0 .. 35, lower triangle of the 8 x 8 tile grid, row-wise) of S -= X X^T
+__device__ __forceinline__ void chain_syrk_tile(double* __restrict__ S, const double* __restrict__ X, int t, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  int mt = 0;
+  while (t > mt) { t -= mt + 1; ++mt; }
+  const int nt = t;
+  double* cp = S + (8 * mt + g) * C_LD + 8 * nt + 2 * q;
+  double2 v = *reinterpret_cast<const double2*>(cp);
+  const double* arow = X + (8 * mt + g) * C_LD + q;
+  const double* brow = X + (8 * nt + g) * C_LD + q;
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) dmma884(v.x, v.y, -arow[4 * k4], brow[4 * k4]);
+  *reinterpret_cast<double2*>(cp) = v;
+}
+
+__device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char* dsm) {
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>(dsm);
+  __shared__ unsigned s_ct[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 4) s_ct[tid] = 0;
+  const MatView none{nullptr, 0, 0};
+  const long long ld = P.L.ld;
+  double* Lg = P.L.p;
+  auto rstart = [&](int b) { return dag_rstart(b, P.n, P.rows, P.nblk); };
+  auto cs = [&](int k) { return min(NB, P.n - k * NB); };
+  chain_load_tile<D_THREADS>(sm.bufS, Lg, ld, rstart(1) - rstart(0), cs(0), tid);     // A(0, 0)
+  __syncthreads();
+  for (int j = 0; j < P.nblk; ++j) {
+    const int i1 = j + 1;
+    const bool has_r1 = i1 < P.nrb, r1_col = i1 < P.nblk;
+    const int r1 = rstart(i1), nr = has_r1 ? rstart(i1 + 1) - r1 : 0;
+    double* Xcur = sm.bufX[j & 1];
+    const double* Xold = sm.bufX[(j & 1) ^ 1];
+    unsigned long long t0 = 0;
+    if (P.trace && (tid == 0 || tid == 384)) t0 = globaltimer();
+    if (warp < 12) {
+      // ---- the sweep of diagonal block j (input: bufS) ----
+      diag_factor_block<false, true>(sm.diag, P.L, 0, j, P.n, P.dinv, P.nblk, none, 0, P.status, nullptr, sm.bufS);
+      fence_proxy_async();
+      diag_sync<true>();
+      if (tid == 0) {
+        __threadfence();
+        st_release(P.upd + j * P.nblk + j, j + 1);
+        st_release(P.chain_pos, j + 1);
+        if (P.trace) s_ct[0] = (unsigned)(globaltimer() - t0);
+      }
+    } else {
+      // ---- background: row block j + 1 ----
+      const int bt = tid - 12 * 32, bw = warp - 12;
+      auto bg_sync = [&]() { asm volatile("bar.sync 5, 128;\n" ::: "memory"); };
+      if (has_r1) {
+        if (bw == 0) {        // the helpers have applied every source k < j - 1 to the three tiles
+          const int want = max(0, j - 1);
+          bool ok;
+          do {
+            ok = true;
+            if (lane == 0 && j >= 1) ok = (ld_acquire(P.upd + i1 * P.nblk + (j - 1)) == want);
+            if (lane == 1) ok = (ld_acquire(P.upd + i1 * P.nblk + j) == want);
+            if (lane == 2 && r1_col) ok = (ld_acquire(P.upd + i1 * P.nblk + i1) == want);
+          } while (!__all_sync(0xffffffffu, ok));
+        }
+        bg_sync();
+        if (P.trace && bt == 0) s_ct[1] = (unsigned)(globaltimer() - t0);
+        if (j >= 1) chain_load_tile<128>(sm.bufT, Lg + (long long)r1 * ld + (j - 1) * NB, ld, nr, NB, bt);
+        chain_load_tile<128>(Xcur, Lg + (long long)r1 * ld + j * NB, ld, nr, cs(j), bt);
+      }
+      asm volatile("bar.sync 4, 512;\n" ::: "memory");      // the sweep threads hold block j in registers: bufS is free
+      if (has_r1 && r1_col) chain_load_tile<128>(sm.bufS, Lg + (long long)r1 * ld + i1 * NB, ld, nr, cs(i1), bt);
+      bg_sync();
+      if (has_r1 && j >= 1) {
+        // L(j+1, j-1) = tile * Dinv_{j-1}^T, 16 rows per warp
+        chain_panel_rows(sm.bufT, sm.xprev, 2 * bw, Lg + (long long)r1 * ld + (j - 1) * NB, ld, nr, NB, lane);
+        chain_panel_rows(sm.bufT, sm.xprev, 2 * bw + 1, Lg + (long long)r1 * ld + (j - 1) * NB, ld, nr, NB, lane);
+        fence_proxy_async();
+        bg_sync();
+        if (bt == 0) {
+          __threadfence();
+          st_release(P.upd + i1 * P.nblk + (j - 1), j);
+        }
+        // source j-1 applied to tiles (j+1, j) and (j+1, j+1)
+        chain_update_rows(Xcur, sm.bufT, Xold, 2 * bw, lane);
+        chain_update_rows(Xcur, sm.bufT, Xold, 2 * bw + 1, lane);
+        if (r1_col)
+          for (int t = bw; t < 36; t += 4) chain_syrk_tile(sm.bufS, sm.bufT, t, lane);
+      }
+      if (P.trace && bt == 0) s_ct[2] = (unsigned)(globaltimer() - t0);
+    }
+    __syncthreads();
+    if (P.trace && tid == 0) {
+      const int slot = atomicAdd(P.trace_ctr, 1);
+      if (slot < P.trace_cap) {
+        unsigned long long* w = P.trace + 4 * (size_t)slot;
+        w[0] = (2ull << 48) | ((unsigned long long)j << 32) | (unsigned long long)j << 16;
+        w[1] = t0;
+        w[2] = globaltimer();
+        // sweep end | background flags seen | background end, in units of 16 ns from the start of the step
+        w[3] = (unsigned long long)(s_ct[0] >> 4) | ((unsigned long long)(s_ct[1] >> 4) << 20) |
+               ((unsigned long long)(s_ct[2] >> 4) << 40);
+      }
+    }
+    if (has_r1) {
+      // ---- critical: L(j+1, j) = tile * Dinv_j^T (warps 0-7, 8 rows each); the other warps save Dinv_j ----
+      if (warp < 8) {
+        chain_panel_rows(Xcur, sm.diag.Xt, warp, Lg + (long long)r1 * ld + j * NB, ld, nr, cs(j), lane);
+        fence_proxy_async();
+      } else {
+        for (int e = tid - 256; e < DIAG_LOW * DIAG_TS / 2; e += 256)
+          reinterpret_cast<double2*>(sm.xprev)[e] = reinterpret_cast<const double2*>(sm.diag.Xt)[e];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(P.upd + i1 * P.nblk + j, j + 1);
+      }
+      // ---- critical: S = A(j+1, j+1) - L(j+1, j) L(j+1, j)^T, the input of the next sweep ----
+      if (r1_col) {
+        for (int t = warp; t < 36; t += 16) chain_syrk_tile(sm.bufS, Xcur, t, lane);
+        __syncthreads();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(D_THREADS, 1)
+potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmD, const DagParams P) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0) {
+    dag_chain_band(P, dsm);
+    return;
+  }
+  // ================================ workers: two sub-workers per CTA =====================================
+  const int sw = tid >> 8, wtid = tid & 255, warp = wtid >> 5, lane = tid & 31;
+  double* pipe = reinterpret_cast<double*>(dsm + (size_t)sw * D_SUB_SMEM);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dsm + 2 * D_SUB_SMEM) + sw * 2 * D_STAGES;
+  unsigned long long* full = bars;
+  unsigned long long* empty = bars + D_STAGES;
+  __shared__ DagTask s_task[2];
+  __shared__ int s_have[2];
+  if (wtid == 0) {
+    for (int s = 0; s < D_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    mbar_fence_init();
+  }
+  sub_barrier(sw);
+  unsigned kbase = 0;
+  // scheduler state (meaningful in warp 0 of the sub-worker only, uniform across its lanes)
+  DagTask hb;
+  bool hb_valid = false, b_done = (P.nq == 0);
+  int seg_lo = 0;
+  hb.type = 1;
+  auto trace_task = [&](const DagTask& t, unsigned long long t0) {
+    const int slot = atomicAdd(P.trace_ctr, 1);
+    if (slot < P.trace_cap) {
+      unsigned long long* w = P.trace + 4 * (size_t)slot;
+      w[0] = ((unsigned long long)t.type << 48) | ((unsigned long long)t.cb << 32) | ((unsigned long long)t.rb << 16) |
+             ((unsigned long long)(t.nrb == 1) << 15) | ((unsigned long long)t.k0 << 8) | (unsigned long long)(t.k1 - t.k0);
+      w[1] = t0;
+      w[2] = globaltimer();
+      w[3] = smid() * 2 + sw;
+    }
+  };
+  // the row task in progress: rows [rt.rb, rt.rb + rt.nrb) against source column rt.cb; rt_c = the column of its next
+  // sub-step (rt.cb: the panel product; then the near columns rt.k0 .. rt.k1-1, left to right)
+  DagTask rt;
+  bool rt_valid = false;
+  int rt_c = 0;
+  rt.type = 2; rt.rb = rt.nrb = rt.cb = rt.k0 = rt.k1 = 0;
+  auto row_sub = [&](const DagTask& r, int c) {
+    DagTask sub;
+    sub.pad0 = sub.pad1 = 0;
+    const int rlast = r.rb + r.nrb - 1;
+    if (c == r.cb) {
+      sub.type = 0; sub.rb = r.rb; sub.nrb = r.nrb; sub.cb = r.cb; sub.k0 = sub.k1 = 0;
+    } else {
+      sub.type = 1; sub.cb = (short)c; sub.k0 = r.cb; sub.k1 = (short)(r.cb + 1);
+      sub.rb = (short)max((int)r.rb, c);                   // a block above the diagonal is not touched
+      sub.nrb = (short)(rlast - sub.rb + 1);
+    }
+    return sub;
+  };
+  for (;;) {
+    if (warp == 0) {
+      int have = 0;
+      DagTask run = hb;
+      while (!have) {
+        // ---- 1. the row task in progress: its next sub-step ----
+        if (rt_valid) {
+          const DagTask sub = row_sub(rt, rt_c);
+          if (dag_ready(sub, P.upd, P.nblk, lane)) { run = sub; have = 2; break; }
+          // A sub-worker holds ONE item, a row task or a bulk ticket, never both: the links of a row's dependency chain
+          // follow each other within microseconds and the chain CTA cannot run faster than the rows below it, so a
+          // holder of a row task only polls (a 40 us bulk task in between would be added to the row's period).
+          // Deadlock freedom: row tasks wait for earlier row tasks (claimed in order, each polled by its holder), the
+          // chain and bulk updates; bulk tickets are taken in an order in which every predecessor on the same tile is
+          // taken first, by sub-workers that hold nothing else; and at most active_cap sub-workers hold row tasks.
+          continue;
+        } else if (!hb_valid && seg_lo < P.nblk) {
+          // ---- 2. claim a row task of the lowest released column that still has unclaimed ones ----
+          const int pos = ld_acquire(P.chain_pos);
+          if (seg_lo < pos) {
+            const bool room = ld_relaxed(P.active) < P.active_cap;
+            for (int s = seg_lo; s < pos && !rt_valid; ++s) {
+              const int base = P.useg[s], size = P.useg[s + 1] - base;
+              int tkt = size;
+              const int head = ld_relaxed(P.uhead + s);
+              if (!room && head >= 3 && head < size) break;     // only the tasks of the row next to the band pass the cap
+              if (head < size) {
+                if (lane == 0) tkt = atomicAdd(P.uhead + s, 1);
+                tkt = __shfl_sync(0xffffffffu, tkt, 0);
+              }
+              if (tkt < size) {
+                rt = P.utasks[base + tkt];
+                rt_valid = true;
+                rt_c = (rt.type == 3) ? rt.k0 : rt.cb;
+                if (lane == 0) atomicAdd(P.active, 1);
+              } else if (s == seg_lo) {
+                ++seg_lo;
+              }
+            }
+            if (rt_valid) continue;
+          }
+        }
+        // ---- 3. the bulk slot ----
+        if (hb_valid && dag_ready(hb, P.upd, P.nblk, lane)) { run = hb; hb_valid = false; have = 1; break; }
+        if (!hb_valid && !b_done) {
+          // Bulk queues: one per source outer block, each ordered by target column; a queue is released when the chain
+          // has published the last column of its block.  The updates of a block commute, so the only deadline of a
+          // bulk update is the panel product of its target column: the head with the smallest target column goes first
+          // (earliest deadline first), and a backlog of far-right updates of old blocks never delays the columns the
+          // chain is about to reach.  Lane m inspects queue m.
+          const int pos = ld_acquire(P.chain_pos);
+          unsigned key = 0xffffffffu;
+          bool exhausted = true;
+          if (lane < P.nq) {
+            const int base = P.bseg[lane], size = P.bseg[lane + 1] - base;
+            const int h = ld_relaxed(P.bhead + lane);
+            if (h < size) {
+              exhausted = false;
+              if (pos >= min(OUTER * (lane + 1), P.nblk)) key = ((unsigned)P.btasks[base + h].cb << 8) | (unsigned)lane;
+            }
+          }
+          const unsigned best = __reduce_min_sync(0xffffffffu, key);
+          if (__all_sync(0xffffffffu, exhausted)) {
+            b_done = true;
+            continue;
+          }
+          if (best != 0xffffffffu) {
+            const int m = (int)(best & 0xffu);
+            const int base = P.bseg[m], size = P.bseg[m + 1] - base;
+            int tkt = 0;
+            if (lane == 0) tkt = atomicAdd(P.bhead + m, 1);
+            tkt = __shfl_sync(0xffffffffu, tkt, 0);
+            if (tkt < size) {
+              hb = P.btasks[base + tkt];
+              hb_valid = true;
+            }
+            continue;
+          }
+        }
+        if (!rt_valid && !hb_valid && b_done && seg_lo >= P.nblk) { have = -1; break; }
+        __nanosleep(64);
+      }
+      if (have == 2) {
+        // bookkeeping of the row task: next sub-step, or done
+        const int rlast = rt.rb + rt.nrb - 1;
+        rt_c = (rt_c == rt.cb) ? rt.k0 : rt_c + 1;
+        if (rt_c >= rt.k1 || rt_c > rlast) rt_valid = false;
+      }
+      if (lane == 0) {
+        s_task[sw] = run;
+        s_have[sw] = have | ((have == 2 && !rt_valid) ? 4 : 0);
+      }
+    }
+    sub_barrier(sw);
+    const int have = s_have[sw];
+    if (have < 0) break;
+    const DagTask t = s_task[sw];
+    unsigned long long t0 = 0;
+    if (P.trace && wtid == 0) t0 = globaltimer();
+    if (t.nrb == 1) dag_execute<true>(t, P, &tmA, &tmB, &tmD, pipe, full, empty, kbase, sw, wtid);
+    else dag_execute<false>(t, P, &tmA, &tmB, &tmD, pipe, full, empty, kbase, sw, wtid);
+    if (P.trace && wtid == 0) trace_task(t, t0);
+    if ((have & 4) && wtid == 0) atomicSub(P.active, 1);      // last sub-step of a row task
+    sub_barrier(sw);      // s_task / s_have may be rewritten only after everybody has read them
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side: the task lists
+// ---------------------------------------------------------------------------------------------------
+// Source-column chunks applied to target column c, in order.  Columns of the same 256-wide outer block and the
+// first NEAR_EXTRA columns of the next one are updated column by column (K = 64, as soon as each source column is
+// final: nothing waits at an outer-block boundary); everything further right gets one K = 256 update per outer block.
+static void chunks_of(int c, int near_extra, std::vector<std::pair<int, int>>& out) {
+  out.clear();
+  const int mc = c / OUTER;
+  for (int m = 0; m < mc; ++m) {
+    if (c - (m + 1) * OUTER < near_extra) {
+      for (int k = m * OUTER; k < (m + 1) * OUTER; ++k) out.emplace_back(k, k + 1);
+    } else {
+      out.emplace_back(m * OUTER, (m + 1) * OUTER);
+    }
+  }
+  for (int k = mc * OUTER; k < c; ++k) out.emplace_back(k, k + 1);
+}
+
+int dag_plan_build(DagPlan& plan, int n, int extra_rows) {
+  dag_plan_free(plan);
+  plan.n = n;
+  plan.rows = n + extra_rows;
+  plan.nblk = ceil_div(n, NB);
+  plan.nrb = plan.nblk + (extra_rows > 0 ? 1 : 0);
+  // SPW_DAG_NEAR: how many columns of the next outer block are still updated column by column (>= 2: the chain CTA
+  // relies on sources c-2, c-1 of every column c being single-column updates).  Larger values give the K = 256
+  // updates more time between becoming ready and being needed, at the price of more K = 64 work.
+  const char* env_ne = getenv("SPW_DAG_NEAR");
+  const int near_extra = std::min(OUTER, std::max(2, env_ne ? atoi(env_ne) : 4));
+  // SPW_DAG_ROW_BLOCKS: row blocks per row task (1: 64-row tiles on all four tensor pipes, the lowest latency per
+  // link of a row's dependency chain; 2: 128-row tiles)
+  const char* env_rb = getenv("SPW_DAG_ROW_BLOCKS");
+  const int row_blocks = (env_rb && env_rb[0] == '2') ? 2 : 1;
+  int dev = 0;
+  SPW_CUDA(cudaGetDevice(&dev));
+  SPW_CUDA(cudaDeviceGetAttribute(&plan.grid, cudaDevAttrMultiProcessorCount, dev));
+  const int nblk = plan.nblk, nrb = plan.nrb;
+  std::vector<std::vector<DagTask>> useg(nblk);
+  std::vector<DagTask> bulk;
+  std::vector<std::pair<int, int>> ch;
+  // bulk queues: one per source outer block m, ordered by target column, then rows (two-block tiles)
+  std::vector<int> boff;
+  for (int m = 0; (m + 1) * OUTER < nblk; ++m) {
+    boff.push_back((int)bulk.size());
+    for (int c = (m + 1) * OUTER; c < nblk; ++c) {
+      chunks_of(c, near_extra, ch);
+      for (auto& kk : ch)
+        if (kk.second - kk.first > 1 && kk.first == m * OUTER) {
+          DagTask t;
+          memset(&t, 0, sizeof(t));
+          t.type = 1; t.cb = (short)c; t.k0 = (short)kk.first; t.k1 = (short)kk.second;
+          for (int b = c; b < nrb; b += 2) {
+            t.rb = (short)b; t.nrb = (short)std::min(2, nrb - b);
+            bulk.push_back(t);
+          }
+        }
+    }
+  }
+  boff.push_back((int)bulk.size());
+  plan.nq = (int)boff.size() - 1;
+  if (plan.nq > 32) { set_error("potrf_dag: order %d too large (more than 32 outer blocks)", n); return SPW_ERR_ARG; }
+  // row tasks: segment j = one task per row tile below the band of the chain CTA (row blocks >= j + 3), from the
+  // diagonal downwards.  A row task does the panel product of its rows against column j and then applies source j
+  // to its rows of the near columns j+1 .. near_end(j) (those that receive single-column updates from j, see
+  // chunks_of), left to right.
+  for (int j = 0; j < nblk; ++j) {
+    const int near_end = std::min(nblk - 1, (j / OUTER) * OUTER + OUTER - 1 + near_extra);
+    int b = j + 3;
+    if (b < nrb) {
+      // the row block next to the band (the chain CTA consumes it two steps later): its three updates run in parallel
+      // on three sub-workers (types 3: updates only; they start when the panel product of the first task is out)
+      DagTask t;
+      memset(&t, 0, sizeof(t));
+      t.cb = (short)j; t.rb = (short)b; t.nrb = 1;
+      for (int c = j + 1; c <= std::min(near_end, b); ++c) {
+        t.type = (short)(c == j + 1 ? 2 : 3);
+        t.k0 = (short)c; t.k1 = (short)(c + 1);
+        useg[j].push_back(t);
+      }
+      if (near_end < j + 1) {      // no near column at all (last column): the panel product alone
+        t.type = 2; t.k0 = (short)(j + 1); t.k1 = (short)(j + 1);
+        useg[j].push_back(t);
+      }
+      ++b;
+    }
+    for (; b < nrb; b += row_blocks) {
+      DagTask t;
+      memset(&t, 0, sizeof(t));
+      t.type = 2; t.cb = (short)j; t.rb = (short)b; t.nrb = (short)std::min(row_blocks, nrb - b);
+      t.k0 = (short)(j + 1); t.k1 = (short)(near_end + 1);
+      useg[j].push_back(t);
+    }
+  }
+  std::vector<DagTask> ut;
+  std::vector<int> off(nblk + 1, 0);
+  for (int j = 0; j < nblk; ++j) {
+    off[j] = (int)ut.size();
+    ut.insert(ut.end(), useg[j].begin(), useg[j].end());
+  }
+  off[nblk] = (int)ut.size();
+  plan.n_urgent = (int)ut.size();
+  plan.n_bulk = (int)bulk.size();
+  SPW_CUDA(cudaMalloc(&plan.d_utasks, sizeof(DagTask) * std::max<size_t>(1, ut.size())));
+  SPW_CUDA(cudaMalloc(&plan.d_btasks, sizeof(DagTask) * std::max<size_t>(1, bulk.size())));
+  SPW_CUDA(cudaMalloc(&plan.d_useg, sizeof(int) * (nblk + 1)));
+  if (!ut.empty()) SPW_CUDA(cudaMemcpy(plan.d_utasks, ut.data(), sizeof(DagTask) * ut.size(), cudaMemcpyHostToDevice));
+  if (!bulk.empty()) SPW_CUDA(cudaMemcpy(plan.d_btasks, bulk.data(), sizeof(DagTask) * bulk.size(), cudaMemcpyHostToDevice));
+  SPW_CUDA(cudaMemcpy(plan.d_useg, off.data(), sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice));
+  SPW_CUDA(cudaMalloc(&plan.d_bseg, sizeof(int) * boff.size()));
+  SPW_CUDA(cudaMemcpy(plan.d_bseg, boff.data(), sizeof(int) * boff.size(), cudaMemcpyHostToDevice));
+  plan.sync_ints = (size_t)nrb * nblk + nblk + plan.nq + 4;
+  // at most this many row tasks run at once: the other sub-workers stay available for the bulk updates the row
+  // tasks may be waiting for (deadlock freedom, see the header comment)
+  plan.active_cap = std::max(1, 2 * (plan.grid - 1) * 2 / 3);
+  SPW_CUDA(cudaMalloc(&plan.d_sync, sizeof(int) * plan.sync_ints));
+  const char* env_tr = getenv("SPW_DAG_TRACE");
+  if (env_tr && env_tr[0] == '1') {
+    plan.trace_cap = plan.n_urgent * (2 + OUTER + near_extra) + plan.n_bulk + nblk + 16;
+    SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 4 * plan.trace_cap));
+  }
+  static bool attr_set[64] = {false};
+  if (!attr_set[dev & 63]) {
+    SPW_CUDA(cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM));
+    attr_set[dev & 63] = true;
+  }
+  return SPW_OK;
+}
+
+void dag_plan_free(DagPlan& plan) {
+  if (plan.d_utasks) cudaFree(plan.d_utasks);
+  if (plan.d_btasks) cudaFree(plan.d_btasks);
+  if (plan.d_useg) cudaFree(plan.d_useg);
+  if (plan.d_bseg) cudaFree(plan.d_bseg);
+  if (plan.d_sync) cudaFree(plan.d_sync);
+  if (plan.d_trace) cudaFree(plan.d_trace);
+  plan = DagPlan();
+}
+
+int potrf_dag(const DagPlan& plan, MatView L, double* dinv, int* status, cudaStream_t st) {
+  MatView dv{dinv, NB, (long long)plan.nblk * NB * NB};
+  CUtensorMap tmA, tmB, tmD;
+  SPW_TRY(make_tensor_map(&tmA, L, plan.n, plan.rows, 1, D_LDS, D_BM));
+  SPW_TRY(make_tensor_map(&tmB, L, plan.n, plan.rows, 1, D_LDS, D_BN));
+  SPW_TRY(make_tensor_map(&tmD, dv, NB, plan.nblk * NB, 1, D_LDS, D_BN));
+  SPW_CUDA(cudaMemsetAsync(plan.d_sync, 0, sizeof(int) * plan.sync_ints, st));
+  DagParams P;
+  P.utasks = plan.d_utasks;
+  P.useg = plan.d_useg;
+  P.btasks = plan.d_btasks;
+  P.bseg = plan.d_bseg;
+  P.nq = plan.nq;
+  P.upd = plan.d_sync;
+  P.uhead = plan.d_sync + (size_t)plan.nrb * plan.nblk;
+  P.bhead = P.uhead + plan.nblk;
+  P.chain_pos = P.bhead + plan.nq;
+  P.trace_ctr = P.chain_pos + 1;
+  P.active = P.chain_pos + 2;
+  P.active_cap = plan.active_cap;
+  P.L = L;
+  P.dinv = dinv;
+  P.n = plan.n;
+  P.rows = plan.rows;
+  P.nblk = plan.nblk;
+  P.nrb = plan.nrb;
+  P.status = status;
+  P.trace = plan.d_trace;
+  P.trace_cap = plan.trace_cap;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(D_THREADS);
+  cfg.dynamicSmemBytes = D_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs resident at once: the workers spin on flags
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPW_CUDA(cudaLaunchKernelEx(&cfg, potrf_dag_kernel, tmA, tmB, tmD, P));
+  SPW_LAUNCHED();
+  return SPW_OK;
+}
+
+int dag_trace_read(const DagPlan& plan, std::vector<unsigned long long>& out) {
+  out.clear();
+  if (!plan.d_trace) return SPW_OK;
+  int cnt = 0;
+  SPW_CUDA(cudaMemcpy(&cnt, plan.d_sync + (size_t)plan.nrb * plan.nblk + plan.nblk + plan.nq + 1, sizeof(int),
+                      cudaMemcpyDeviceToHost));
+  cnt = std::min(cnt, plan.trace_cap);
+  out.resize(4 * (size_t)cnt);
+  if (cnt > 0) SPW_CUDA(cudaMemcpy(out.data(), plan.d_trace, sizeof(unsigned long long) * 4 * cnt, cudaMemcpyDeviceToHost));
+  return SPW_OK;
+}
+
+}  // namespace spw
