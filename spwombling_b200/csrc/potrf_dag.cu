@@ -1,4 +1,6 @@
-// Single-matrix blocked Cholesky as ONE persistent cooperative kernel (sm_100a, fp64).
+// Single-matrix blocked Cholesky as ONE persistent cooperative kernel (sm_100a, fp64).  EXPERIMENTAL: opt-in with
+// SPW_DAG=1; the multi-launch shadow schedule of linalg.cu is still faster at N = 5000 (2.74 ms against 3.2 ms per
+// factorisation on the same box, see DESIGN.md section 4 for the per-task traces behind every decision below).
 //
 // Why: the chain of hlmBayes_sp (R/hlmBayes_sp.R:114,140,181) factors one matrix of order N+1 per proposal, strictly
 // one after the other.  As a sequence of launches the factorisation is bound by its critical path (79 diagonal
@@ -6,19 +8,23 @@
 // stream edges between ~400 small kernels.  Here the dependencies live in global-memory flags instead:
 //
 //   * CTA 0 ("chain") factors and inverts the 64 x 64 diagonal blocks one after the other (the warp-role sweep of
-//     diag_factor.cuh) and publishes each block with a release store;
-//   * every other CTA holds two independent 8-warp "sub-workers" (the 128 x 64 TMA-fed DMMA tile engine of
-//     linalg.cu; two per SM so that one hides the C read-modify-write of the other).  A sub-worker never blocks:
-//     its first warp keeps up to one claimed *urgent* task (panel products and K = 64 updates, queued per source
-//     column and released when the chain has published that column) and one claimed *bulk* task (K = 256 trailing
-//     updates, one global queue), polls their flags, and runs whichever becomes ready -- urgent first;
-//   * flags: upd[row block][column block] counts the source columns already applied to that 64 x 64 block; the
-//     panel product of column c needs upd == c and leaves c + 1 ("final").  An update waits for its operand blocks
-//     to be final and for the previous update of its own block.
+//     diag_factor.cuh) and owns the two row blocks below each of them (dag_chain_band);
+//   * every other CTA holds two independent 8-warp "sub-workers" (the 128 x 64 / 64 x 64 TMA-fed DMMA tile engine;
+//     two per SM so that one hides the epilogue of the other).  A sub-worker holds ONE item at a time:
+//       - a row task: one row tile against one source column -- its panel product, then the K = 64 updates of the
+//         near columns, left to right, on the same sub-worker (the links of a row's dependency chain, panel(k) ->
+//         update(k+1) -> panel(k+1), are the latency every row shares with the chain).  Queued per source column,
+//         released when the chain has published that column, taken by ticket in row order;
+//       - or a bulk task (K = 256 update), from one queue per source outer block, earliest deadline first.
+//   * every block accumulates its bulk updates in a separate buffer and its single-column updates in place, each in
+//     source order (deterministic), merged once (see dag_s0 / dag_merges): a late bulk update never holds up the
+//     single-column updates of the same block.
+//   * flags: upd[row block][column block] / fb[...] count the source columns applied; the panel product of column c
+//     needs upd == c and leaves c + 1 ("final").
 //
-// Both queues are in topological order and claims are made in order, so the earliest unfinished task is always
-// either running, held by a worker that polls it, or claimable by a worker with a free slot: no deadlock as long
-// as all CTAs are resident, which the cooperative launch guarantees.
+// Deadlock freedom: row tasks and bulk tickets are taken in topological order; a holder polls only its own item; at
+// most active_cap sub-workers hold row tasks, so bulk updates always find sub-workers; all CTAs are resident
+// (cooperative launch).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -75,7 +81,9 @@ struct DagParams {
   const DagTask* btasks;   // bulk tasks, one queue per source outer block: queue m = [bseg[m], bseg[m+1]), by target column
   const int* bseg;
   int nq;
-  int* upd;        // [nrb][nblk]
+  int* upd;        // [nrb][nblk]: main flags (single-column updates and panel products of a block)
+  int* fb;         // [nrb][nblk]: source columns accumulated into the bulk buffer of a block
+  double* Bp;      // bulk accumulator, same layout as L
   int* uhead;      // [nblk]
   int* bhead;      // [nq]
   int* chain_pos;  // 1
@@ -94,26 +102,44 @@ __device__ __forceinline__ int dag_rstart(int b, int n, int rows, int nblk) {
   return b <= nblk ? min(b * NB, n) : rows;
 }
 
-// Flag word of a 64 x 64 block: the number of source columns applied to it so far (in any order: the updates of a
-// block commute), c + 1 once the panel product of column c has made it final, and a lock bit that an update holds
-// only while its epilogue reads, modifies and writes the block.
-constexpr int FLAG_LOCK = 1 << 30;
+// Every block below the diagonal accumulates its updates in TWO places, each strictly in source-column order (the
+// result is deterministic):
+//   * the K = 256 bulk updates of the sources [0, s0(c)) go to the bulk buffer B (first one stores, the others add);
+//     fb[block] = sources accumulated so far;
+//   * the single-column updates of the sources [s0(c), c) are subtracted from the block in place;
+//     upd[block] = 0 before the first one, k + 1 after source k, c + 1 ("final") after the panel product.
+// The two are merged (block -= B) exactly once: by the last single-column update (source c - 1) -- or, for the three
+// blocks of a row that the chain CTA takes over, when it loads them.  A late bulk update therefore never holds up the
+// single-column updates of the same block; its only deadline is that merge.
+__device__ __forceinline__ int dag_s0(int c) { return OUTER * max(0, c / OUTER - 1); }
+// does this single-column update merge the bulk buffer?  (last source of the column, rows below the chain's band)
+__device__ __forceinline__ bool dag_merges(const DagTask& t) {
+  return t.type == 1 && t.k1 - t.k0 == 1 && t.k0 == t.cb - 1 && t.rb >= t.cb + 3 && dag_s0(t.cb) > 0;
+}
 
 // One polling round over the flags a task depends on (warp-collective; every lane reads at most one flag).
 //   panel product of column c: the diagonal block is published; every source column < c has been applied to its blocks
-//   update: its operand blocks are final (the block itself is locked in the epilogue, not here)
-__device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, int nblk, int lane) {
+//   update: the previous update of the same kind on its block(s) is done; its operand blocks are final
+__device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, const int* fb, int nblk, int lane) {
+  const int* f = upd;
   int b = -1, c = 0, want = 0;
   if (t.type == 0) {
     if (lane == 0) { b = t.cb; c = t.cb; want = t.cb + 1; }
     else if (lane <= t.nrb) { b = t.rb + lane - 1; c = t.cb; want = t.cb; }
   } else {
     const int nk = t.k1 - t.k0, na = t.nrb * nk;
-    if (lane < na) { b = t.rb + lane / nk; c = t.k0 + lane % nk; want = c + 1; }
-    else if (lane < na + nk) { b = t.cb; c = t.k0 + (lane - na); want = c + 1; }
+    if (lane < t.nrb) {
+      b = t.rb + lane; c = t.cb;
+      if (nk > 1) { f = fb; want = t.k0; }
+      else want = (t.k0 == dag_s0(t.cb)) ? 0 : t.k0;
+    } else if (lane < t.nrb + na) { const int i = lane - t.nrb; b = t.rb + i / nk; c = t.k0 + i % nk; want = c + 1; }
+    else if (lane < t.nrb + na + nk) { b = t.cb; c = t.k0 + (lane - t.nrb - na); want = c + 1; }
+    else if (lane < 2 * t.nrb + na + nk && dag_merges(t)) {
+      b = t.rb + (lane - t.nrb - na - nk); c = t.cb; f = fb; want = dag_s0(t.cb);
+    }
   }
   bool ok = true;
-  if (b >= 0) ok = (ld_acquire(upd + b * nblk + c) == want);
+  if (b >= 0) ok = (ld_acquire(f + b * nblk + c) == want);
   return __all_sync(0xffffffffu, ok);
 }
 
@@ -184,45 +210,45 @@ __device__ __forceinline__ void dag_execute(const DagTask& t, const DagParams& P
     if (lane == 0) mbar_arrive(&empty[s]);
   }
   kbase += nkt;
-  // ---- epilogue: panel: C = acc; update: C -= acc under the lock of its block(s) (lower row block first).  C may have
-  //      been written by another SM during this launch: read it past L1 (ld.global.cg) ----
-  int held[2] = {0, 0};
-  if (!panel) {
-    if (wtid == 0) {
-      for (int i = 0; i < t.nrb; ++i) {
-        int* f = P.upd + (t.rb + i) * P.nblk + t.cb;
-        for (;;) {
-          const int v = ld_acquire(f);
-          if (!(v & FLAG_LOCK) && atomicCAS(f, v, v | FLAG_LOCK) == v) { held[i] = v; break; }
-        }
-      }
-      __threadfence();
-    }
-    sub_barrier(sw);
-  }
-  double* Cp = P.L.p + (long long)row0 * P.L.ld + c0;
+  // ---- epilogue.  panel: C = acc.  single-column update: C -= acc (and -= B when it merges the bulk buffer).
+  //      bulk update: B = acc (first source block) or B += acc.  The blocks may have been written by other SMs during
+  //      this launch: read them past L1 (ld.global.cg) ----
+  const bool bulk = !panel && (t.k1 - t.k0 > 1);
+  const bool merge = dag_merges(t);
+  const bool first_bulk = bulk && t.k0 == 0;
+  double* Cp = (bulk ? P.Bp : P.L.p) + (long long)row0 * P.L.ld + c0;
+  const double* Bq = P.Bp + (long long)row0 * P.L.ld + c0;
   if (live) {
 #pragma unroll
     for (int i = 0; i < MF; ++i) {
       const int r = warp_m * 32 + i * 8 + g;
       if (r >= m) continue;
       double* crow = Cp + (long long)r * P.L.ld;
+      const double* brow = Bq + (long long)r * P.L.ld;
       double2 old[NF];
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
         const int c = warp_n * WN + j * 8 + 2 * q;
         old[j] = make_double2(0.0, 0.0);
-        if (!panel && c < ncol) {
+        if (!panel && !first_bulk && c < ncol) {
           if (c + 1 < ncol) old[j] = __ldcg(reinterpret_cast<const double2*>(crow + c));
           else old[j].x = __ldcg(crow + c);
+          if (merge) {
+            if (c + 1 < ncol) {
+              const double2 bv = __ldcg(reinterpret_cast<const double2*>(brow + c));
+              old[j].x -= bv.x; old[j].y -= bv.y;
+            } else {
+              old[j].x -= __ldcg(brow + c);
+            }
+          }
         }
       }
 #pragma unroll
       for (int j = 0; j < NF; ++j) {
         const int c = warp_n * WN + j * 8 + 2 * q;
         if (c >= ncol) continue;
-        const double v0 = panel ? acc[i][j][0] : old[j].x - acc[i][j][0];
-        const double v1 = panel ? acc[i][j][1] : old[j].y - acc[i][j][1];
+        const double v0 = panel ? acc[i][j][0] : (bulk ? old[j].x + acc[i][j][0] : old[j].x - acc[i][j][0]);
+        const double v1 = panel ? acc[i][j][1] : (bulk ? old[j].y + acc[i][j][1] : old[j].y - acc[i][j][1]);
         if (c + 1 < ncol) __stcg(reinterpret_cast<double2*>(crow + c), make_double2(v0, v1));
         else __stcg(crow + c, v0);
       }
@@ -232,11 +258,11 @@ __device__ __forceinline__ void dag_execute(const DagTask& t, const DagParams& P
   sub_barrier(sw);
   if (wtid == 0) {
     __threadfence();
-    for (int i = 0; i < t.nrb; ++i)
-      st_release(P.upd + (t.rb + i) * P.nblk + t.cb, panel ? t.cb + 1 : held[i] + (t.k1 - t.k0));
+    int* f = bulk ? P.fb : P.upd;
+    const int val = panel ? t.cb + 1 : t.k1;
+    for (int i = 0; i < t.nrb; ++i) st_release(f + (t.rb + i) * P.nblk + t.cb, val);
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // The chain CTA in band mode: it owns the diagonal blocks AND the two row blocks below each of them.
@@ -262,25 +288,35 @@ struct ChainSmem {
 };
 static_assert(sizeof(ChainSmem) <= D_SMEM, "chain state must fit");
 
+// dst = src (- sub, when the block has a bulk accumulator to merge)
 template <int NT>
-__device__ __forceinline__ void chain_load_tile(double* __restrict__ dst, const double* __restrict__ src, long long ld,
-                                                int nr, int nc, int t) {
-  // all loads of a thread are issued before the first store: one L2 round trip per tile, not one per element
-  constexpr int PER = NB * (NB / 2) / NT;
-  double2 v[PER];
+__device__ __forceinline__ void chain_load_tile(double* __restrict__ dst, const double* __restrict__ src,
+                                                const double* __restrict__ sub, long long ld, int nr, int nc, int t) {
+  // all loads of a batch are issued before the first use: a few L2 round trips per tile, not one per element
+  constexpr int PER = NB * (NB / 2) / NT, BATCH = PER < 8 ? PER : 8;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int e = t + i * NT, r = e >> 5, c = (e & 31) * 2;
-    v[i] = make_double2(0.0, 0.0);
-    if (r < nr) {
-      if (c + 1 < nc) v[i] = __ldcg(reinterpret_cast<const double2*>(src + (long long)r * ld + c));
-      else if (c < nc) v[i].x = __ldcg(src + (long long)r * ld + c);
+  for (int i0 = 0; i0 < PER; i0 += BATCH) {
+    double2 v[BATCH], w[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = t + (i0 + i) * NT, r = e >> 5, c = (e & 31) * 2;
+      v[i] = w[i] = make_double2(0.0, 0.0);
+      if (r < nr) {
+        const long long o = (long long)r * ld + c;
+        if (c + 1 < nc) {
+          v[i] = __ldcg(reinterpret_cast<const double2*>(src + o));
+          if (sub) w[i] = __ldcg(reinterpret_cast<const double2*>(sub + o));
+        } else if (c < nc) {
+          v[i].x = __ldcg(src + o);
+          if (sub) w[i].x = __ldcg(sub + o);
+        }
+      }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int e = t + i * NT, r = e >> 5, c = (e & 31) * 2;
-    *reinterpret_cast<double2*>(dst + r * C_LD + c) = v[i];
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = t + (i0 + i) * NT, r = e >> 5, c = (e & 31) * 2;
+      *reinterpret_cast<double2*>(dst + r * C_LD + c) = make_double2(v[i].x - w[i].x, v[i].y - w[i].y);
+    }
   }
 }
 
@@ -366,7 +402,8 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
   double* Lg = P.L.p;
   auto rstart = [&](int b) { return dag_rstart(b, P.n, P.rows, P.nblk); };
   auto cs = [&](int k) { return min(NB, P.n - k * NB); };
-  chain_load_tile<D_THREADS>(sm.bufS, Lg, ld, rstart(1) - rstart(0), cs(0), tid);     // A(0, 0)
+  const double* Bg = P.Bp;
+  chain_load_tile<D_THREADS>(sm.bufS, Lg, nullptr, ld, rstart(1) - rstart(0), cs(0), tid);     // A(0, 0)
   __syncthreads();
   for (int j = 0; j < P.nblk; ++j) {
     const int i1 = j + 1;
@@ -392,7 +429,9 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
       const int bt = tid - 12 * 32, bw = warp - 12;
       auto bg_sync = [&]() { asm volatile("bar.sync 5, 128;\n" ::: "memory"); };
       if (has_r1) {
-        if (bw == 0) {        // the helpers have applied every source k < j - 1 to the three tiles
+        if (bw == 0) {
+          // the helpers have applied every source k < j - 1 to the three blocks: the single-column updates in place
+          // (main flag) and the bulk updates in the bulk buffer (fb), which is merged while loading
           const int want = max(0, j - 1);
           bool ok;
           do {
@@ -400,15 +439,27 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
             if (lane == 0 && j >= 1) ok = (ld_acquire(P.upd + i1 * P.nblk + (j - 1)) == want);
             if (lane == 1) ok = (ld_acquire(P.upd + i1 * P.nblk + j) == want);
             if (lane == 2 && r1_col) ok = (ld_acquire(P.upd + i1 * P.nblk + i1) == want);
+            if (lane == 3 && j >= 1) ok = (ld_acquire(P.fb + i1 * P.nblk + (j - 1)) == dag_s0(j - 1));
+            if (lane == 4) ok = (ld_acquire(P.fb + i1 * P.nblk + j) == dag_s0(j));
+            if (lane == 5 && r1_col) ok = (ld_acquire(P.fb + i1 * P.nblk + i1) == dag_s0(i1));
           } while (!__all_sync(0xffffffffu, ok));
         }
         bg_sync();
         if (P.trace && bt == 0) s_ct[1] = (unsigned)(globaltimer() - t0);
-        if (j >= 1) chain_load_tile<128>(sm.bufT, Lg + (long long)r1 * ld + (j - 1) * NB, ld, nr, NB, bt);
-        chain_load_tile<128>(Xcur, Lg + (long long)r1 * ld + j * NB, ld, nr, cs(j), bt);
+        if (j >= 1) {
+          const long long o = (long long)r1 * ld + (j - 1) * NB;
+          chain_load_tile<128>(sm.bufT, Lg + o, dag_s0(j - 1) > 0 ? Bg + o : nullptr, ld, nr, NB, bt);
+        }
+        {
+          const long long o = (long long)r1 * ld + j * NB;
+          chain_load_tile<128>(Xcur, Lg + o, dag_s0(j) > 0 ? Bg + o : nullptr, ld, nr, cs(j), bt);
+        }
       }
       asm volatile("bar.sync 4, 512;\n" ::: "memory");      // the sweep threads hold block j in registers: bufS is free
-      if (has_r1 && r1_col) chain_load_tile<128>(sm.bufS, Lg + (long long)r1 * ld + i1 * NB, ld, nr, cs(i1), bt);
+      if (has_r1 && r1_col) {
+        const long long o = (long long)r1 * ld + i1 * NB;
+        chain_load_tile<128>(sm.bufS, Lg + o, dag_s0(i1) > 0 ? Bg + o : nullptr, ld, nr, cs(i1), bt);
+      }
       bg_sync();
       if (has_r1 && j >= 1) {
         // L(j+1, j-1) = tile * Dinv_{j-1}^T, 16 rows per warp
@@ -533,7 +584,7 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---- 1. the row task in progress: its next sub-step ----
         if (rt_valid) {
           const DagTask sub = row_sub(rt, rt_c);
-          if (dag_ready(sub, P.upd, P.nblk, lane)) { run = sub; have = 2; break; }
+          if (dag_ready(sub, P.upd, P.fb, P.nblk, lane)) { run = sub; have = 2; break; }
           // A sub-worker holds ONE item, a row task or a bulk ticket, never both: the links of a row's dependency chain
           // follow each other within microseconds and the chain CTA cannot run faster than the rows below it, so a
           // holder of a row task only polls (a 40 us bulk task in between would be added to the row's period).
@@ -568,13 +619,15 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // ---- 3. the bulk slot ----
-        if (hb_valid && dag_ready(hb, P.upd, P.nblk, lane)) { run = hb; hb_valid = false; have = 1; break; }
+        if (hb_valid && dag_ready(hb, P.upd, P.fb, P.nblk, lane)) { run = hb; hb_valid = false; have = 1; break; }
         if (!hb_valid && !b_done) {
-          // Bulk queues: one per source outer block, each ordered by target column; a queue is released when the chain
-          // has published the last column of its block.  The updates of a block commute, so the only deadline of a
-          // bulk update is the panel product of its target column: the head with the smallest target column goes first
-          // (earliest deadline first), and a backlog of far-right updates of old blocks never delays the columns the
-          // chain is about to reach.  Lane m inspects queue m.
+          // Bulk queues: one per source outer block m, each ordered by target column c; a queue is released when the
+          // chain has published the last column of its block.  The bulk updates of one block are applied in source
+          // order, one after the other (~30 us each), and must all be in when the block is merged, i.e. when the chain
+          // reaches column block q = c / 4: the head with the smallest 5 q + 3 m goes first (earliest deadline once the
+          // chunks still to follow on the same block are counted at ~1.5 chain steps each).  Smallest c alone leaves
+          // all chunks of a block to the last moment, in sequence; smallest m alone lets a backlog of far-right updates
+          // of old blocks delay the columns the chain is about to reach.  Lane m inspects queue m.
           const int pos = ld_acquire(P.chain_pos);
           unsigned key = 0xffffffffu;
           bool exhausted = true;
@@ -583,7 +636,8 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int h = ld_relaxed(P.bhead + lane);
             if (h < size) {
               exhausted = false;
-              if (pos >= min(OUTER * (lane + 1), P.nblk)) key = ((unsigned)P.btasks[base + h].cb << 8) | (unsigned)lane;
+              if (pos >= min(OUTER * (lane + 1), P.nblk))
+                key = ((unsigned)(5 * (P.btasks[base + h].cb / OUTER) + 3 * lane) << 8) | (unsigned)lane;
             }
           }
           const unsigned best = __reduce_min_sync(0xffffffffu, key);
@@ -657,15 +711,14 @@ int dag_plan_build(DagPlan& plan, int n, int extra_rows) {
   plan.rows = n + extra_rows;
   plan.nblk = ceil_div(n, NB);
   plan.nrb = plan.nblk + (extra_rows > 0 ? 1 : 0);
-  // SPW_DAG_NEAR: how many columns of the next outer block are still updated column by column (>= 2: the chain CTA
-  // relies on sources c-2, c-1 of every column c being single-column updates).  Larger values give the K = 256
-  // updates more time between becoming ready and being needed, at the price of more K = 64 work.
-  const char* env_ne = getenv("SPW_DAG_NEAR");
-  const int near_extra = std::min(OUTER, std::max(2, env_ne ? atoi(env_ne) : 4));
-  // SPW_DAG_ROW_BLOCKS: row blocks per row task (1: 64-row tiles on all four tensor pipes, the lowest latency per
-  // link of a row's dependency chain; 2: 128-row tiles)
-  const char* env_rb = getenv("SPW_DAG_ROW_BLOCKS");
-  const int row_blocks = (env_rb && env_rb[0] == '2') ? 2 : 1;
+  // the columns of an outer block receive single-column updates from the sources of their own and of the previous
+  // outer block (device side: dag_s0), K = 256 bulk updates from everything older
+  const int near_extra = OUTER;
+  // Row tasks within `near_rows` row blocks of the diagonal are one-block (64-row) tiles on all four tensor pipes: the
+  // lowest latency per link of a row's dependency chain, for the rows the chain reaches soon.  Further down two-block
+  // tiles do the same work in fewer, more efficient tasks (SPW_DAG_NEAR_ROWS, default: every row task is one block).
+  const char* env_nr = getenv("SPW_DAG_NEAR_ROWS");
+  const int near_rows = env_nr ? atoi(env_nr) : 1 << 20;
   int dev = 0;
   SPW_CUDA(cudaGetDevice(&dev));
   SPW_CUDA(cudaDeviceGetAttribute(&plan.grid, cudaDevAttrMultiProcessorCount, dev));
@@ -718,12 +771,16 @@ int dag_plan_build(DagPlan& plan, int n, int extra_rows) {
       }
       ++b;
     }
-    for (; b < nrb; b += row_blocks) {
+    while (b < nrb) {
+      // two-block tiles start at an even distance from column j so that the same pairs recur in every segment of
+      // their life (a block must not change partner while updates of the pair are in flight in the same column)
+      const int nb = (b - j - 3 >= near_rows && ((b & 1) == 0) && b + 1 < nrb) ? 2 : 1;
       DagTask t;
       memset(&t, 0, sizeof(t));
-      t.type = 2; t.cb = (short)j; t.rb = (short)b; t.nrb = (short)std::min(row_blocks, nrb - b);
+      t.type = 2; t.cb = (short)j; t.rb = (short)b; t.nrb = (short)nb;
       t.k0 = (short)(j + 1); t.k1 = (short)(near_end + 1);
       useg[j].push_back(t);
+      b += nb;
     }
   }
   std::vector<DagTask> ut;
@@ -743,7 +800,9 @@ int dag_plan_build(DagPlan& plan, int n, int extra_rows) {
   SPW_CUDA(cudaMemcpy(plan.d_useg, off.data(), sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice));
   SPW_CUDA(cudaMalloc(&plan.d_bseg, sizeof(int) * boff.size()));
   SPW_CUDA(cudaMemcpy(plan.d_bseg, boff.data(), sizeof(int) * boff.size(), cudaMemcpyHostToDevice));
-  plan.sync_ints = (size_t)nrb * nblk + nblk + plan.nq + 4;
+  plan.sync_ints = 2 * (size_t)nrb * nblk + nblk + plan.nq + 4;
+  plan.ld = round_up_ll(n, 16);
+  SPW_CUDA(cudaMalloc(&plan.d_bulk, sizeof(double) * (size_t)plan.rows * plan.ld));
   // at most this many row tasks run at once: the other sub-workers stay available for the bulk updates the row
   // tasks may be waiting for (deadlock freedom, see the header comment)
   plan.active_cap = std::max(1, 2 * (plan.grid - 1) * 2 / 3);
@@ -767,6 +826,7 @@ void dag_plan_free(DagPlan& plan) {
   if (plan.d_useg) cudaFree(plan.d_useg);
   if (plan.d_bseg) cudaFree(plan.d_bseg);
   if (plan.d_sync) cudaFree(plan.d_sync);
+  if (plan.d_bulk) cudaFree(plan.d_bulk);
   if (plan.d_trace) cudaFree(plan.d_trace);
   plan = DagPlan();
 }
@@ -784,8 +844,11 @@ int potrf_dag(const DagPlan& plan, MatView L, double* dinv, int* status, cudaStr
   P.btasks = plan.d_btasks;
   P.bseg = plan.d_bseg;
   P.nq = plan.nq;
+  if (L.ld != plan.ld) { set_error("potrf_dag: leading dimension %lld, plan expects %lld", L.ld, plan.ld); return SPW_ERR_ARG; }
   P.upd = plan.d_sync;
-  P.uhead = plan.d_sync + (size_t)plan.nrb * plan.nblk;
+  P.fb = plan.d_sync + (size_t)plan.nrb * plan.nblk;
+  P.Bp = plan.d_bulk;
+  P.uhead = P.fb + (size_t)plan.nrb * plan.nblk;
   P.bhead = P.uhead + plan.nblk;
   P.chain_pos = P.bhead + plan.nq;
   P.trace_ctr = P.chain_pos + 1;
@@ -820,7 +883,7 @@ int dag_trace_read(const DagPlan& plan, std::vector<unsigned long long>& out) {
   out.clear();
   if (!plan.d_trace) return SPW_OK;
   int cnt = 0;
-  SPW_CUDA(cudaMemcpy(&cnt, plan.d_sync + (size_t)plan.nrb * plan.nblk + plan.nblk + plan.nq + 1, sizeof(int),
+  SPW_CUDA(cudaMemcpy(&cnt, plan.d_sync + 2 * (size_t)plan.nrb * plan.nblk + plan.nblk + plan.nq + 1, sizeof(int),
                       cudaMemcpyDeviceToHost));
   cnt = std::min(cnt, plan.trace_cap);
   out.resize(4 * (size_t)cnt);

@@ -27,9 +27,11 @@ struct DagPlan {
   DagTask* d_btasks = nullptr;    // bulk tasks (K = 256 updates): one queue per source outer block
   int* d_bseg = nullptr;          // nq + 1 offsets into d_btasks
   int nq = 0;
-  int* d_sync = nullptr;          // flags [nrb][nblk] | claim counters of the urgent segments [nblk] and of the bulk
+  int* d_sync = nullptr;          // flags [nrb][nblk] x 2 (in place / bulk buffer) | claim counters of the urgent segments [nblk] and of the bulk
                                   // queues [nq] | chain position | trace counter
   size_t sync_ints = 0;
+  double* d_bulk = nullptr;       // accumulator of the K = 256 updates (same layout as the matrix; merged once per block)
+  long long ld = 0;
   unsigned long long* d_trace = nullptr;   // optional (SPW_DAG_TRACE=1): 4 words per executed task
   int trace_cap = 0;
   int grid = 0;                   // CTAs of the persistent kernel (== SM count)

@@ -181,3 +181,47 @@ def test_gradient_run_p_matches_gradient_run():
     rc = lib.spw_gradient_run_p(_ip(2), _ip(n), ptr(coords), _ip(g), ptr(grid), _ip(S), ptr(phi), ptr(sig2), ptr(z),
                                 ptr(eps), _ip(1), _ip(3), _dp(0.95), _ip(0), None, ptr(s2), ptr(i1), ctypes.byref(st))
     assert rc == 0 and np.array_equal(s0, s2)
+
+
+_DAG_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import spwombling_b200 as spw
+from oracle.hlm import hlm_bayes_sp, r_chol
+import oracle
+for n in (257, 300, 1100, 1985):
+    rng = np.random.Generator(np.random.Philox(n))
+    coords = rng.random((n, 2))
+    A = oracle.cov_matern1(oracle.dist_matrix(coords), 8.0, 2.0) + 0.5 * np.eye(n)
+    U, half = spw.chol(A)
+    Uo = r_chol(A)
+    assert np.max(np.abs(U - Uo)) / np.max(np.abs(Uo)) < 1e-11, n
+    U2, _ = spw.chol(A)
+    assert np.array_equal(U, U2), "the persistent kernel must be deterministic"
+n, niter = 1100, 4
+rng = np.random.Generator(np.random.Philox(77))
+coords = rng.random((n, 2))
+y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
+y = y - y.mean()
+norm, unif = rng.standard_normal(3 * niter), rng.random(3 * niter)
+ref = hlm_bayes_sp(y, coords, niter=niter, nburn=1, report=2, cov_type="matern2", norm=norm, unif=unif, trgt_fn_compute=True)
+out = spw.hlmBayes_sp(y=y, coords=coords, niter=niter, nburn=1, report=2, cov_type="matern2", norm=norm, unif=unif,
+                      trgtFn_compute=True, verbose=False)
+for key in ("sig2", "tau2", "phi"):
+    np.testing.assert_allclose(out["diagnostics"]["chain"][key], ref["chain"][key], rtol=1e-10)
+np.testing.assert_allclose(out["trgt_fn"], ref["trgt_fn"], rtol=1e-10)
+print("ok")
+"""
+
+
+def test_persistent_tile_dag_cholesky_against_oracle():
+    """The opt-in persistent single-matrix Cholesky (SPW_DAG=1; the switch is read per call but plans are cached per
+    process, hence the subprocess): ragged orders, the appended y row of the hlm system, run-to-run determinism."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPW_DAG="1", SPW_DAG_MIN="200")
+    res = subprocess.run([sys.executable, "-c", _DAG_SCRIPT % {"root": root}], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-4000:]
