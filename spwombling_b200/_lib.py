@@ -82,6 +82,19 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise ImportError("libspwombling.so not found at %s -- run `python -m spwombling_b200.build` "
                           "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+    if "SPW_NCCL_PATH" not in os.environ:
+        # the in-process multi-GPU gather dlopen()s NCCL at run time: prefer the copy PyTorch bundles (found without
+        # importing torch), or a later `import torch` would meet the older system libnccl.so.2 under the same soname
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations or []) if spec else []:
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["SPW_NCCL_PATH"] = cand
+                    break
+        except Exception:       # pragma: no cover
+            pass
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -1,5 +1,6 @@
 // C ABI of libspwombling: argument checking, device workspaces, host<->device marshalling of R-layout
 // arrays, and the per-shard driver of the spatial_gradient pipeline.  See include/spwombling.h.
+#include <atomic>
 #include <cstdarg>
 #include <ctime>
 #include <cstdlib>
@@ -20,13 +21,14 @@
 #include "linalg.cuh"
 #include "potrf_dag.cuh"
 #include "summary.cuh"
+#include "tma.cuh"
 
 namespace spw {
 
 static thread_local char tl_error[1024] = "";
 static char g_error[1024] = "";
 static std::mutex g_err_mu;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 static long long g_ws_limit = 0;
 
 void set_error(const char* fmt, ...) {
@@ -98,6 +100,10 @@ struct DeviceCtx {
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
   size_t ws2_bytes = 0;
+  void* io = nullptr;          // grow-only device staging of the host-pointer entry points (inputs, draws, moments)
+  size_t io_bytes = 0;
+  void* io2 = nullptr;         // grow-only gather / R-layout buffers on the root device
+  size_t io2_bytes = 0;
   Lookahead la;                // second stream + events of the single-matrix Cholesky's lookahead schedule
 };
 static DeviceCtx g_ctx[64];
@@ -199,6 +205,17 @@ static int get_workspace(DeviceCtx& c, size_t bytes, void** out) {
   return SPW_OK;
 }
 
+static int grow_buffer(void** p, size_t* have, size_t bytes) {
+  if (bytes > *have) {
+    if (*p) SPW_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    SPW_CUDA(cudaMalloc(p, bytes));
+    *have = bytes;
+  }
+  return SPW_OK;
+}
+
 static int get_scratch(DeviceCtx& c, size_t bytes, void** out) {
   if (bytes > c.ws2_bytes) {
     if (c.ws2) SPW_CUDA(cudaFree(c.ws2));
@@ -257,10 +274,15 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   const size_t per_sample_fixed = 2 * mat + (size_t)ld * sizeof(double) + (size_t)nblk * NB * NB * sizeof(double) + 64;
   const size_t at_per_g = (size_t)c * ld * sizeof(double);
   // the (B, gc) decision is cached per problem shape so that repeated calls skip cudaMemGetInfo
-  struct ShapeKey { int type, n, G, S; size_t limit; int B, gc; };
-  static thread_local ShapeKey last = {-1, 0, 0, 0, 0, 0, 0};
-  const bool reuse = (last.type == type && last.n == n && last.G == G && last.S == S && last.limit == (size_t)g_ws_limit &&
-                      ctx->ws_bytes > 0);
+  struct ShapeKey { int dev, type, n, G, S; size_t limit; int B, gc; };
+  static thread_local ShapeKey last = {-1, -1, 0, 0, 0, 0, 0, 0};
+  int cur_dev = 0;
+  SPW_CUDA(cudaGetDevice(&cur_dev));
+  // reuse only on the same device and only while the cached choice still fits the workspace this context already owns
+  // (otherwise the budget is consulted again: other allocations may have grown since)
+  const bool reuse = (last.dev == cur_dev && last.type == type && last.n == n && last.G == G && last.S == S &&
+                      last.limit == (size_t)g_ws_limit &&
+                      ctx->ws_bytes >= (per_sample_fixed + at_per_g * (size_t)last.gc) * (size_t)last.B + 4096);
   const size_t budget = reuse ? 0 : workspace_budget();
   int gc = std::min(G, 65535);
   int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / (per_sample_fixed + at_per_g * gc));
@@ -279,7 +301,7 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
     gc = gc / 16 * 16;
     if (gc < 16) { set_error("spw_gradient: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
   }
-  last = ShapeKey{type, n, G, S, (size_t)g_ws_limit, B, gc};
+  last = ShapeKey{cur_dev, type, n, G, S, (size_t)g_ws_limit, B, gc};
   const LinalgPlan* plan;
   SPW_TRY(get_plan(*ctx, n, 0, B < 4 ? 1 : 0, &plan));
   const size_t total = (per_sample_fixed + at_per_g * gc) * B + 4096;
@@ -449,7 +471,14 @@ static bool nccl_load() {
   tried = true;
   const char* env = getenv("SPW_NCCL");
   if (env && env[0] == '0') return false;
-  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  // SPW_NCCL_PATH: an explicit library (the Python host points it at the copy PyTorch bundles, so that a later
+  // `import torch` in the same process finds the NCCL it was built against under the shared soname); then whatever is
+  // already mapped; then the system library
+  void* h = nullptr;
+  const char* path = getenv("SPW_NCCL_PATH");
+  if (path && path[0]) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
   if (!h) return false;
   g_nccl.CommInitAll = (int (*)(NcclApi::comm_t*, int, const int*))dlsym(h, "ncclCommInitAll");
@@ -467,21 +496,33 @@ static bool nccl_load() {
 // The path's one exchange step as an NCCL collective over NVLink: every device d > 0 sends its [S_d][c][g] block,
 // device 0 receives them into the sample-major gather buffer (grouped ncclSend / ncclRecv, datatype ncclFloat64 = 8).
 // Returns SPW_OK, or a negative value when NCCL is unavailable (the caller then uses peer copies).
-static int nccl_gather(int ngpu, const std::vector<const double*>& src, const std::vector<size_t>& count,
-                       const std::vector<double*>& dst_on_root) {
+// communicator clique over devices 0 .. ngpu-1 (cached); false when NCCL is unavailable.  Called from a side thread
+// at the start of spw_gradient_run so that the set-up overlaps the shards' compute.
+static bool nccl_prepare(int ngpu) {
   std::lock_guard<std::mutex> lk(g_nccl_mu);
-  if (!nccl_load()) return -1;
+  if (!nccl_load()) return false;
   if ((int)g_nccl_comms.size() != ngpu) {
-    for (auto c : g_nccl_comms) g_nccl.CommDestroy(c);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto c : g_nccl_comms)
+      if (c) g_nccl.CommDestroy(c);
     g_nccl_comms.assign(ngpu, nullptr);
     std::vector<int> devs(ngpu);
     for (int d = 0; d < ngpu; ++d) devs[d] = d;
-    int rc = g_nccl.CommInitAll(g_nccl_comms.data(), ngpu, devs.data());
+    const int rc = g_nccl.CommInitAll(g_nccl_comms.data(), ngpu, devs.data());
+    cudaSetDevice(cur);
     if (rc != 0) {
       g_nccl_comms.clear();
-      return -1;
+      return false;
     }
   }
+  return true;
+}
+
+static int nccl_gather(int ngpu, const std::vector<const double*>& src, const std::vector<size_t>& count,
+                       const std::vector<double*>& dst_on_root) {
+  if (!nccl_prepare(ngpu)) return -1;
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
   int rc = g_nccl.GroupStart();
   for (int d = 1; d < ngpu && rc == 0; ++d) {
     if (count[d] == 0) continue;
@@ -549,9 +590,7 @@ int spw_set_workspace_limit(long long bytes) {
 }
 
 long long spw_launch_count(int reset) {
-  long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int spw_last_gather_used_nccl(void) { return g_last_gather_nccl; }
@@ -584,6 +623,7 @@ int spw_profile_read(double* ms, long long* calls, double* main_flops, int reset
 // [4] end of kernel
 int spw_debug_diag_timing(long long* out16) {
   if (!g_diag_dbg) {
+    SPW_CUDA(cudaGetDevice(&g_diag_dbg_device));      // the counters live on (and are only handed to kernels of) this device
     SPW_CUDA(cudaMalloc(&g_diag_dbg, 16 * sizeof(long long)));
     SPW_CUDA(cudaMemset(g_diag_dbg, 0, 16 * sizeof(long long)));
     return SPW_OK;
@@ -615,7 +655,7 @@ int spw_shutdown(void) {
   cudaGetDevice(&cur);
   for (int d = 0; d < ndev && d < 64; ++d) {
     DeviceCtx& c = g_ctx[d];
-    if (!c.stream && !c.ws && c.plans.empty() && c.dag_plans.empty()) continue;
+    if (!c.stream && !c.ws && !c.io && !c.io2 && c.plans.empty() && c.dag_plans.empty()) continue;
     cudaSetDevice(d);
     for (auto& kv : c.plans) {
       plan_free(*kv.second);
@@ -633,6 +673,12 @@ int spw_shutdown(void) {
     if (c.ws2) cudaFree(c.ws2);
     c.ws2 = nullptr;
     c.ws2_bytes = 0;
+    if (c.io) cudaFree(c.io);
+    c.io = nullptr;
+    c.io_bytes = 0;
+    if (c.io2) cudaFree(c.io2);
+    c.io2 = nullptr;
+    c.io2_bytes = 0;
     if (c.stream) cudaStreamDestroy(c.stream);
     c.stream = nullptr;
     if (c.la.bulk) cudaStreamDestroy(c.la.bulk);
@@ -644,6 +690,14 @@ int spw_shutdown(void) {
     c.la.ev_chain.clear();
     c.la.ev_bulk.clear();
   }
+  {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.ok)
+      for (auto c : g_nccl_comms)
+        if (c) g_nccl.CommDestroy(c);
+    g_nccl_comms.clear();
+  }
+  tensor_map_cache_clear();
   cudaSetDevice(cur);
   return SPW_OK;
 }
@@ -838,69 +892,81 @@ int spw_gradient_shard_dev(int type, int n, const double* coords_dev, int g, con
                         ldz, eps_dev, out_draws_dev, out_mean_dev, out_var_dev, info, st);
 }
 
-// one device's share of spw_gradient_run: samples [s_lo, s_hi).  The shard's draws stay on the device
-// (layout [Sl][c][g]) for the gather; moments go straight back to the host.
-struct ShardResult {
-  DevBuf draws;      // [Sl][c][g] on the shard's device (unless written in place into the gather buffer)
-};
+// host wall-clock phases of spw_gradient_run (SPW_TIMING=1 prints them)
+static double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
+// one device's share of spw_gradient_run: samples [s_lo, s_hi).  The shard's draws stay on the device
+// (layout [Sl][c][g], in the context's grow-only staging buffer or in place in the gather buffer) for the gather;
+// moments go straight back to the host.
 static int gradient_run_one(int device, int type, int n, const double* coords, int g, const double* grid, int S,
                             int s_lo, int s_hi, const double* phi, const double* sig2, const double* z,
-                            const double* eps, bool want_draws, double* draws_inplace, ShardResult* res,
-                            double* out_mean, double* out_var, int* info) {
+                            const double* eps, bool want_draws, double* draws_inplace, double** shard_draws,
+                            double* out_mean, double* out_var, int* info, double* t_setup_ms) {
+  const double t0 = wall_ms();
   SPW_CUDA(cudaSetDevice(device));
   DeviceCtx* ctx;
   SPW_TRY(get_ctx(&ctx));
   cudaStream_t st = ctx->stream;
   const int c = ncomp_of(type), Sl = s_hi - s_lo;
+  *shard_draws = nullptr;
   if (Sl <= 0) return SPW_OK;
   const long long ldz = pad_ld(n);
-  DevBuf dc, dg, dphi, dsig, dzr, dz, deps, dmean, dvar;
-  SPW_TRY(dc.alloc(sizeof(double) * 2 * n));
-  SPW_TRY(dg.alloc(sizeof(double) * 2 * g));
-  SPW_TRY(dphi.alloc(sizeof(double) * Sl));
-  SPW_TRY(dsig.alloc(sizeof(double) * Sl));
-  SPW_TRY(dzr.alloc(sizeof(double) * (size_t)Sl * n));
-  SPW_TRY(dz.alloc(sizeof(double) * (size_t)Sl * ldz));
-  SPW_CUDA(cudaMemcpyAsync(dc.p, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-  SPW_CUDA(cudaMemcpyAsync(dg.p, grid, sizeof(double) * 2 * g, cudaMemcpyHostToDevice, st));
-  SPW_CUDA(cudaMemcpyAsync(dphi.p, phi + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
-  SPW_CUDA(cudaMemcpyAsync(dsig.p, sig2 + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
-  // model$z is S x n column-major: bring rows s_lo..s_hi of every column, then transpose to [Sl][ldz]
-  SPW_CUDA(cudaMemcpy2DAsync(dzr.p, sizeof(double) * Sl, z + s_lo, sizeof(double) * S, sizeof(double) * Sl, n,
-                             cudaMemcpyHostToDevice, st));
-  SPW_TRY(transpose_batched(n, Sl, dzr.as<double>(), Sl, 0, dz.as<double>(), ldz, 0, 1, st));
+  const size_t n_units = (size_t)Sl * g * c;
+  // one grow-only staging allocation per device instead of ~10 cudaMalloc / cudaFree pairs per call
+  size_t need = 4096 + sizeof(double) * (2 * (size_t)n + 2 * (size_t)g + 2 * (size_t)Sl + (size_t)Sl * n + (size_t)Sl * ldz) + 8 * 256;
+  if (want_draws) need += sizeof(double) * n_units * (draws_inplace ? 1 : 2) + 2 * 256;
+  if (out_mean) need += sizeof(double) * n_units + 256;
+  if (out_var) need += sizeof(double) * n_units * c + 256;
+  SPW_TRY(grow_buffer(&ctx->io, &ctx->io_bytes, need));
+  Carver cv(ctx->io);
+  double* dc = cv.take<double>(2 * (size_t)n);
+  double* dg = cv.take<double>(2 * (size_t)g);
+  double* dphi = cv.take<double>(Sl);
+  double* dsig = cv.take<double>(Sl);
+  double* dzr = cv.take<double>((size_t)Sl * n);
+  double* dz = cv.take<double>((size_t)Sl * ldz);
+  double* deps = want_draws ? cv.take<double>(n_units) : nullptr;
   double* ddraw = nullptr;
-  if (want_draws) {
-    SPW_TRY(deps.alloc(sizeof(double) * (size_t)Sl * g * c));
-    SPW_CUDA(cudaMemcpyAsync(deps.p, eps + (size_t)s_lo * g * c, sizeof(double) * (size_t)Sl * g * c,
+  if (want_draws) ddraw = draws_inplace ? draws_inplace : cv.take<double>(n_units);
+  double* dmean = out_mean ? cv.take<double>(n_units) : nullptr;
+  double* dvar = out_var ? cv.take<double>(n_units * c) : nullptr;
+  SPW_CUDA(cudaMemcpyAsync(dc, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dg, grid, sizeof(double) * 2 * g, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dphi, phi + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dsig, sig2 + s_lo, sizeof(double) * Sl, cudaMemcpyHostToDevice, st));
+  // model$z is S x n column-major: bring rows s_lo..s_hi of every column, then transpose to [Sl][ldz]
+  SPW_CUDA(cudaMemcpy2DAsync(dzr, sizeof(double) * Sl, z + s_lo, sizeof(double) * S, sizeof(double) * Sl, n,
                              cudaMemcpyHostToDevice, st));
-    if (draws_inplace) {
-      ddraw = draws_inplace;
-    } else {
-      SPW_TRY(res->draws.alloc(sizeof(double) * (size_t)Sl * g * c));
-      ddraw = res->draws.as<double>();
-    }
-  }
-  if (out_mean) SPW_TRY(dmean.alloc(sizeof(double) * (size_t)Sl * g * c));
-  if (out_var) SPW_TRY(dvar.alloc(sizeof(double) * (size_t)Sl * g * c * c));
-  int rc = gradient_shard(type, n, dc.as<double>(), dc.as<double>() + n, g, dg.as<double>(), dg.as<double>() + g, Sl,
-                          dphi.as<double>(), dsig.as<double>(), dz.as<double>(), (int)ldz,
-                          want_draws ? deps.as<double>() : nullptr, ddraw,
-                          out_mean ? dmean.as<double>() : nullptr, out_var ? dvar.as<double>() : nullptr, info, st);
+  SPW_TRY(transpose_batched(n, Sl, dzr, Sl, 0, dz, ldz, 0, 1, st));
+  if (want_draws)
+    SPW_CUDA(cudaMemcpyAsync(deps, eps + (size_t)s_lo * g * c, sizeof(double) * n_units, cudaMemcpyHostToDevice, st));
+  if (t_setup_ms) *t_setup_ms = wall_ms() - t0;
+  int rc = gradient_shard(type, n, dc, dc + n, g, dg, dg + g, Sl, dphi, dsig, dz, (int)ldz, deps, ddraw, dmean, dvar,
+                          info, st);
   if (rc != SPW_OK) {
     if (info && info[0] > 0) info[0] += s_lo;
     return rc;
   }
   if (out_mean)
-    SPW_CUDA(cudaMemcpyAsync(out_mean + (size_t)s_lo * g * c, dmean.p, sizeof(double) * (size_t)Sl * g * c,
-                             cudaMemcpyDeviceToHost, st));
+    SPW_CUDA(cudaMemcpyAsync(out_mean + (size_t)s_lo * g * c, dmean, sizeof(double) * n_units, cudaMemcpyDeviceToHost, st));
   if (out_var)
-    SPW_CUDA(cudaMemcpyAsync(out_var + (size_t)s_lo * g * c * c, dvar.p, sizeof(double) * (size_t)Sl * g * c * c,
+    SPW_CUDA(cudaMemcpyAsync(out_var + (size_t)s_lo * g * c * c, dvar, sizeof(double) * n_units * c,
                              cudaMemcpyDeviceToHost, st));
   SPW_CUDA(cudaStreamSynchronize(st));
+  *shard_draws = ddraw;
   return SPW_OK;
 }
+
+// restores the caller's current device on every exit path
+struct DeviceRestore {
+  int dev = -1;
+  DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
+  ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
 
 int spw_gradient_run(int type, int n, const double* coords, int g, const double* grid, int S, const double* phi,
                      const double* sig2, const double* z, const double* eps, int ngpu, int nbatch, double prob,
@@ -919,28 +985,44 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
   if (ngpu < 1) ngpu = 1;
   if (ngpu > ndev) { set_error("spw_gradient_run: ngpu = %d but only %d devices", ngpu, ndev); return SPW_ERR_ARG; }
   if (ngpu > S) ngpu = S;
-  int root = 0;
-  SPW_CUDA(cudaGetDevice(&root));
-  if (ngpu > 1) root = 0;
+  static const bool timing = getenv("SPW_TIMING") && getenv("SPW_TIMING")[0] == '1';
+  const double t_begin = wall_ms();
+  DeviceRestore restore;       // the caller's device is current again when this function returns
+  int root = restore.dev < 0 ? 0 : restore.dev;
+  if (ngpu > 1) root = 0;      // shards run on devices 0 .. ngpu-1, the gather goes to device 0
   const int c = ncomp_of(type);
-  // gather buffer on the root device: all draws, sample-major [S][c][g]
+  const size_t n_all = (size_t)S * g * c;
+  // gather buffer on the root device: all draws, sample-major [S][c][g] (+ the R-layout copy and the summary)
   SPW_CUDA(cudaSetDevice(root));
   DeviceCtx* rctx;
   SPW_TRY(get_ctx(&rctx));
   cudaStream_t rst = rctx->stream;
-  DevBuf dall, dr, dsum;
-  if (want_draws) SPW_TRY(dall.alloc(sizeof(double) * (size_t)S * g * c));
+  double *dall = nullptr, *dr = nullptr, *dsum = nullptr;
+  if (want_draws) {
+    size_t need = sizeof(double) * n_all + 4096;
+    if (out_draws) need += sizeof(double) * n_all + 256;
+    if (out_summary) need += sizeof(double) * 3 * (size_t)g * c + 256;
+    SPW_TRY(grow_buffer(&rctx->io2, &rctx->io2_bytes, need));
+    Carver cv(rctx->io2);
+    dall = cv.take<double>(n_all);
+    if (out_draws) dr = cv.take<double>(n_all);
+    if (out_summary) dsum = cv.take<double>(3 * (size_t)g * c);
+  }
   auto lo_of = [&](int d) { return (int)((long long)S * d / ngpu); };
+  // the NCCL clique is created while the shards compute (communicator set-up takes seconds on 8 GPUs)
+  std::thread nccl_init;
+  if (ngpu > 1 && want_draws) nccl_init = std::thread([ngpu]() { nccl_prepare(ngpu); });
   // contiguous sample shards, one host thread per device (R/spatial_gradient.R:29-32,200)
   std::vector<int> rcs(ngpu, SPW_OK);
   std::vector<std::vector<int>> infos(ngpu, std::vector<int>(4, 0));
   std::vector<std::string> errs(ngpu);
-  std::vector<ShardResult> results(ngpu);
+  std::vector<double*> shard(ngpu, nullptr);
+  std::vector<double> t_setup(ngpu, 0.0);
   auto work = [&](int d) {
     const int dev = (ngpu > 1) ? d : root;
-    double* inplace = (want_draws && dev == root) ? dall.as<double>() + (size_t)lo_of(d) * g * c : nullptr;
+    double* inplace = (want_draws && dev == root) ? dall + (size_t)lo_of(d) * g * c : nullptr;
     rcs[d] = gradient_run_one(dev, type, n, coords, g, grid, S, lo_of(d), lo_of(d + 1), phi, sig2, z, eps, want_draws,
-                              inplace, &results[d], out_mean, out_var, infos[d].data());
+                              inplace, &shard[d], out_mean, out_var, infos[d].data(), &t_setup[d]);
     if (rcs[d] != SPW_OK) errs[d] = tl_error;
   };
   if (ngpu == 1) {
@@ -950,21 +1032,13 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
     for (int d = 0; d < ngpu; ++d) th.emplace_back(work, d);
     for (auto& t : th) t.join();
   }
+  if (nccl_init.joinable()) nccl_init.join();
+  const double t_compute = wall_ms();
   SPW_CUDA(cudaSetDevice(root));
-  auto free_shards = [&]() {   // shard buffers live on their own devices
-    for (int d = 0; d < ngpu; ++d) {
-      if (!results[d].draws.p) continue;
-      cudaSetDevice((ngpu > 1) ? d : root);
-      cudaFree(results[d].draws.p);
-      results[d].draws.p = nullptr;
-    }
-    cudaSetDevice(root);
-  };
   for (int d = 0; d < ngpu; ++d)
     if (rcs[d] != SPW_OK) {
       if (info) memcpy(info, infos[d].data(), sizeof(int) * 4);
       set_error("%s", errs[d].c_str());
-      free_shards();
       return rcs[d];
     }
   if (!want_draws) return SPW_OK;
@@ -976,13 +1050,13 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
     std::vector<size_t> cnt(ngpu, 0);
     std::vector<double*> dst(ngpu, nullptr);
     for (int d = 1; d < ngpu; ++d) {
-      src[d] = results[d].draws.as<double>();
+      src[d] = shard[d];
       cnt[d] = (size_t)(lo_of(d + 1) - lo_of(d)) * g * c;
-      dst[d] = dall.as<double>() + (size_t)lo_of(d) * g * c;
+      dst[d] = dall + (size_t)lo_of(d) * g * c;
     }
     const int nrc = nccl_gather(ngpu, src, cnt, dst);
     if (nrc == SPW_OK) gathered = true;
-    else if (nrc > 0) { free_shards(); return nrc; }
+    else if (nrc > 0) return nrc;
     g_last_gather_nccl = gathered ? 1 : 0;
   }
   for (int d = 0; d < ngpu && !gathered; ++d) {
@@ -994,24 +1068,42 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
       if (pe != cudaSuccess) cudaGetLastError();   // already enabled (or unsupported): the copy still works
     }
     const size_t cnt = (size_t)(lo_of(d + 1) - lo_of(d)) * g * c;
-    SPW_CUDA(cudaMemcpyPeerAsync(dall.as<double>() + (size_t)lo_of(d) * g * c, root, results[d].draws.p, dev,
-                                 sizeof(double) * cnt, rst));
-  }
-  if (out_summary) {
-    SPW_TRY(dsum.alloc(sizeof(double) * 3 * (size_t)g * c));
-    void* scratch;
-    SPW_TRY(get_scratch(*rctx, hpd_scratch_bytes(S, g, c, nbatch), &scratch));
-    SPW_TRY(hpd_summary_dev(S, g, c, nbatch, prob, dall.as<double>(), dsum.as<double>(), scratch, rst));
-    SPW_CUDA(cudaMemcpyAsync(out_summary, dsum.p, sizeof(double) * 3 * (size_t)g * c, cudaMemcpyDeviceToHost, rst));
-  }
-  if (out_draws) {
-    // [S][c][g] -> the c matrices S x g, column-major: out_draws[s + S*(j + g*a)]
-    SPW_TRY(dr.alloc(sizeof(double) * (size_t)S * g * c));
-    SPW_TRY(transpose_batched(S, c * g, dall.as<double>(), (long long)c * g, 0, dr.as<double>(), S, 0, 1, rst));
-    SPW_CUDA(cudaMemcpyAsync(out_draws, dr.p, sizeof(double) * (size_t)S * g * c, cudaMemcpyDeviceToHost, rst));
+    SPW_CUDA(cudaMemcpyPeerAsync(dall + (size_t)lo_of(d) * g * c, root, shard[d], dev, sizeof(double) * cnt, rst));
   }
   SPW_CUDA(cudaStreamSynchronize(rst));
-  free_shards();
+  const double t_gather = wall_ms();
+  if (out_summary) {
+    void* scratch;
+    SPW_TRY(get_scratch(*rctx, hpd_scratch_bytes(S, g, c, nbatch), &scratch));
+    SPW_TRY(hpd_summary_dev(S, g, c, nbatch, prob, dall, dsum, scratch, rst));
+    SPW_CUDA(cudaMemcpyAsync(out_summary, dsum, sizeof(double) * 3 * (size_t)g * c, cudaMemcpyDeviceToHost, rst));
+  }
+  double t_summary = t_gather;
+  if (timing) {
+    SPW_CUDA(cudaStreamSynchronize(rst));
+    t_summary = wall_ms();
+  }
+  if (out_draws) {
+    // [S][c][g] -> the c matrices S x g, column-major: out_draws[s + S*(j + g*a)]; transposed and copied back in
+    // column chunks so that the copy of one chunk overlaps the transpose of the next
+    const size_t cols = (size_t)c * g;
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(cols, ((size_t)64 << 20) / (sizeof(double) * (size_t)S)));
+    for (size_t c0 = 0; c0 < cols; c0 += chunk) {
+      const size_t nc = std::min(chunk, cols - c0);
+      SPW_TRY(transpose_batched(S, (int)nc, dall + c0, (long long)cols, 0, dr + c0 * S, S, 0, 1, rst));
+      SPW_CUDA(cudaMemcpyAsync(out_draws + c0 * S, dr + c0 * S, sizeof(double) * nc * S, cudaMemcpyDeviceToHost, rst));
+    }
+  }
+  SPW_CUDA(cudaStreamSynchronize(rst));
+  if (timing) {
+    const double t_end = wall_ms();
+    double ts = 0.0;
+    for (double v : t_setup) ts = std::max(ts, v);
+    fprintf(stderr, "[spw] spw_gradient_run S=%d g=%d n=%d ngpu=%d: total %.1f ms = shards %.1f (of which set-up + H2D <= %.1f) + "
+            "gather %.1f (%s) + summary %.1f + draws to R layout and D2H %.1f\n", S, g, n, ngpu, t_end - t_begin,
+            t_compute - t_begin, ts, t_gather - t_compute, ngpu == 1 ? "none" : (g_last_gather_nccl == 1 ? "nccl" : "peer copies"),
+            t_summary - t_gather, t_end - t_summary);
+  }
   return SPW_OK;
 }
 

@@ -1,6 +1,7 @@
 // Shared device helpers for libspwombling (sm_100a, fp64).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
@@ -8,7 +9,7 @@ namespace spw {
 
 // ---- error plumbing -------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
-extern long long g_launches;   // kernels launched by this library (spw_launch_count)
+extern std::atomic<long long> g_launches;   // kernels launched by this library (spw_launch_count)
 
 #define SPW_CUDA(call)                                                                        \
   do {                                                                                        \

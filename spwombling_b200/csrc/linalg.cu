@@ -193,6 +193,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // the triangular-inverse buffer) happen once at the end, by all threads.
 // ---------------------------------------------------------------------------------------------------
 long long* g_diag_dbg = nullptr;   // optional device buffer of 16 cycle counters (spw_debug_diag_timing)
+int g_diag_dbg_device = -1;        // the device it was allocated on
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_factor_kernel(MatView L, int blk, int n, double* __restrict__ dinv, int nblk, MatView linv, int has_linv,
@@ -519,12 +520,17 @@ int potrf_batched(const LinalgPlan& plan, MatView L, double* dinv, MatView* linv
     SPW_CUDA(cudaGetDevice(&dev));
     SPW_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
+  long long* dbg = nullptr;
+  if (g_diag_dbg) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == g_diag_dbg_device) dbg = g_diag_dbg;
+  }
   for (int j = 0; j < plan.nblk; ++j) {
     mark();
     const int mb = j / per_outer;                      // outer block of this step
     if (split(mb - 1)) SPW_CUDA(cudaEventRecord(la->ev_chain[j], st));
-    diag_factor_kernel<<<batch, DIAG_THREADS, 0, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status,
-                                                       g_diag_dbg);
+    diag_factor_kernel<<<batch, DIAG_THREADS, 0, st>>>(L, j, plan.n, dinv, plan.nblk, lv, linv ? 1 : 0, status, dbg);
     SPW_LAUNCHED();
     bool rest_wait = false;
     if (split(mb - 1)) {

@@ -47,6 +47,7 @@ struct LinalgPlan {
 
 // single != 0: schedule for one matrix at a time (hlm chain): small tiles on the latency-critical steps
 extern long long* g_diag_dbg;
+extern int g_diag_dbg_device;
 int plan_build(LinalgPlan& plan, int n, int extra_rows, int single);
 void plan_free(LinalgPlan& plan);
 

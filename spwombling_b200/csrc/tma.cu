@@ -40,6 +40,11 @@ struct MapKey {
 static std::vector<std::pair<MapKey, CUtensorMap>> g_map_cache;
 static std::mutex g_map_mu;
 
+void tensor_map_cache_clear() {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  g_map_cache.clear();
+}
+
 int make_tensor_map(CUtensorMap* tm, const MatView& M, int cols, int rows, int batch, int box_cols, int box_rows) {
   const MapKey key{M.p, M.ld, M.stride, cols, rows, batch, box_cols, box_rows};
   {

@@ -49,5 +49,6 @@ __device__ __forceinline__ void named_barrier() {
 // rank-3 fp64 map over a batch of row-major matrices: dims (cols, rows, batch), box (box_cols, box_rows, 1),
 // no swizzle, out-of-range elements read as zero.
 int make_tensor_map(CUtensorMap* tm, const MatView& M, int cols, int rows, int batch, int box_cols, int box_rows);
+void tensor_map_cache_clear();      // spw_shutdown: the cached maps describe buffers that are being freed
 
 }  // namespace spw
