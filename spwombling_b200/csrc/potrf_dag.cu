@@ -42,7 +42,10 @@ constexpr int D_A_STAGE = D_BM * D_LDS, D_B_STAGE = D_BN * D_LDS, D_STAGE = D_A_
 constexpr uint32_t D_STAGE_BYTES = D_STAGE * sizeof(double);
 constexpr size_t D_SUB_SMEM = size_t(D_STAGES) * D_STAGE_BYTES;
 constexpr size_t D_SMEM = 2 * D_SUB_SMEM + 256;
-constexpr int OUTER = OUTER_W / NB;        // source columns per bulk update (4)
+#ifndef SPW_DAG_OUTER
+#define SPW_DAG_OUTER 3
+#endif
+constexpr int OUTER = SPW_DAG_OUTER;       // source columns per bulk update (K = 64 * OUTER); >= 3: see dag_merges
 static_assert(sizeof(DiagSmem) <= 2 * D_SUB_SMEM, "chain CTA state must fit in the worker ring");
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -112,17 +115,22 @@ __device__ __forceinline__ int dag_rstart(int b, int n, int rows, int nblk) {
 // blocks of a row that the chain CTA takes over, when it loads them.  A late bulk update therefore never holds up the
 // single-column updates of the same block; its only deadline is that merge.
 __device__ __forceinline__ int dag_s0(int c) { return OUTER * max(0, c / OUTER - 1); }
-// does this single-column update merge the bulk buffer?  (last source of the column, rows below the chain's band)
+// does this single-column update merge the bulk buffer?  The last one a sub-worker applies to the block: source c - 1,
+// or source R - 3 for the three blocks (R, R-2 .. R) of a row that the chain CTA finishes itself (it applies the
+// sources R - 2, R - 1 in shared memory and never reads the bulk buffer).
 __device__ __forceinline__ bool dag_merges(const DagTask& t) {
-  return t.type == 1 && t.k1 - t.k0 == 1 && t.k0 == t.cb - 1 && t.rb >= t.cb + 3 && dag_s0(t.cb) > 0;
+  return t.type == 1 && t.k1 - t.k0 == 1 && t.nrb == 1 && dag_s0(t.cb) > 0 && t.k0 == min(t.cb - 1, t.rb - 3);
 }
 
 // One polling round over the flags a task depends on (warp-collective; every lane reads at most one flag).
 //   panel product of column c: the diagonal block is published; every source column < c has been applied to its blocks
-//   update: the previous update of the same kind on its block(s) is done; its operand blocks are final
-__device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, const int* fb, int nblk, int lane) {
+//   update: the previous update of the same kind on its block(s) is done; its operand blocks are final; a merging
+//   single-column update also needs the bulk buffer of its block complete
+// Returns 0: ready; 1: waiting for panel products / single-column updates / the chain; 2: waiting for bulk updates only.
+__device__ __forceinline__ int dag_state(const DagTask& t, const int* upd, const int* fb, int nblk, int lane) {
   const int* f = upd;
   int b = -1, c = 0, want = 0;
+  bool bulk_dep = false;
   if (t.type == 0) {
     if (lane == 0) { b = t.cb; c = t.cb; want = t.cb + 1; }
     else if (lane <= t.nrb) { b = t.rb + lane - 1; c = t.cb; want = t.cb; }
@@ -130,20 +138,23 @@ __device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, cons
     const int nk = t.k1 - t.k0, na = t.nrb * nk;
     if (lane < t.nrb) {
       b = t.rb + lane; c = t.cb;
-      if (nk > 1) { f = fb; want = t.k0; }
+      if (nk > 1) { f = fb; want = t.k0; bulk_dep = true; }
       else want = (t.k0 == dag_s0(t.cb)) ? 0 : t.k0;
     } else if (lane < t.nrb + na) { const int i = lane - t.nrb; b = t.rb + i / nk; c = t.k0 + i % nk; want = c + 1; }
     else if (lane < t.nrb + na + nk) { b = t.cb; c = t.k0 + (lane - t.nrb - na); want = c + 1; }
     else if (lane < 2 * t.nrb + na + nk && dag_merges(t)) {
-      b = t.rb + (lane - t.nrb - na - nk); c = t.cb; f = fb; want = dag_s0(t.cb);
+      b = t.rb + (lane - t.nrb - na - nk); c = t.cb; f = fb; want = dag_s0(t.cb); bulk_dep = true;
     }
   }
   bool ok = true;
   if (b >= 0) ok = (ld_acquire(f + b * nblk + c) == want);
-  return __all_sync(0xffffffffu, ok);
+  if (__all_sync(0xffffffffu, ok)) return 0;
+  return __all_sync(0xffffffffu, ok || bulk_dep) ? 2 : 1;
+}
+__device__ __forceinline__ bool dag_ready(const DagTask& t, const int* upd, const int* fb, int nblk, int lane) {
+  return dag_state(t, upd, fb, nblk, lane) == 0;
 }
 
-// ---- the tile engine: C[128 x 64] (+)= alpha * A[128 x K] * B[64 x K]^T, operands by TMA, 8 warps (4 x 2) ----
 // NARROW (one row block, m <= 64): the 8 warps are laid out 2 x 4 (warp tile 32 x 16) so that all four tensor pipes
 // work on the 64 x 64 tile -- these are the tasks next to the band of the chain CTA, whose latency the chain sees.
 template <bool NARROW>
@@ -402,7 +413,6 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
   double* Lg = P.L.p;
   auto rstart = [&](int b) { return dag_rstart(b, P.n, P.rows, P.nblk); };
   auto cs = [&](int k) { return min(NB, P.n - k * NB); };
-  const double* Bg = P.Bp;
   chain_load_tile<D_THREADS>(sm.bufS, Lg, nullptr, ld, rstart(1) - rstart(0), cs(0), tid);     // A(0, 0)
   __syncthreads();
   for (int j = 0; j < P.nblk; ++j) {
@@ -430,8 +440,8 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
       auto bg_sync = [&]() { asm volatile("bar.sync 5, 128;\n" ::: "memory"); };
       if (has_r1) {
         if (bw == 0) {
-          // the helpers have applied every source k < j - 1 to the three blocks: the single-column updates in place
-          // (main flag) and the bulk updates in the bulk buffer (fb), which is merged while loading
+          // the helpers have applied every source k < j - 1 to the three blocks (the last single-column update of each
+          // has merged the bulk buffer of the block)
           const int want = max(0, j - 1);
           bool ok;
           do {
@@ -439,26 +449,23 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
             if (lane == 0 && j >= 1) ok = (ld_acquire(P.upd + i1 * P.nblk + (j - 1)) == want);
             if (lane == 1) ok = (ld_acquire(P.upd + i1 * P.nblk + j) == want);
             if (lane == 2 && r1_col) ok = (ld_acquire(P.upd + i1 * P.nblk + i1) == want);
-            if (lane == 3 && j >= 1) ok = (ld_acquire(P.fb + i1 * P.nblk + (j - 1)) == dag_s0(j - 1));
-            if (lane == 4) ok = (ld_acquire(P.fb + i1 * P.nblk + j) == dag_s0(j));
-            if (lane == 5 && r1_col) ok = (ld_acquire(P.fb + i1 * P.nblk + i1) == dag_s0(i1));
           } while (!__all_sync(0xffffffffu, ok));
         }
         bg_sync();
         if (P.trace && bt == 0) s_ct[1] = (unsigned)(globaltimer() - t0);
         if (j >= 1) {
           const long long o = (long long)r1 * ld + (j - 1) * NB;
-          chain_load_tile<128>(sm.bufT, Lg + o, dag_s0(j - 1) > 0 ? Bg + o : nullptr, ld, nr, NB, bt);
+          chain_load_tile<128>(sm.bufT, Lg + o, nullptr, ld, nr, NB, bt);
         }
         {
           const long long o = (long long)r1 * ld + j * NB;
-          chain_load_tile<128>(Xcur, Lg + o, dag_s0(j) > 0 ? Bg + o : nullptr, ld, nr, cs(j), bt);
+          chain_load_tile<128>(Xcur, Lg + o, nullptr, ld, nr, cs(j), bt);
         }
       }
       asm volatile("bar.sync 4, 512;\n" ::: "memory");      // the sweep threads hold block j in registers: bufS is free
       if (has_r1 && r1_col) {
         const long long o = (long long)r1 * ld + i1 * NB;
-        chain_load_tile<128>(sm.bufS, Lg + o, dag_s0(i1) > 0 ? Bg + o : nullptr, ld, nr, cs(i1), bt);
+        chain_load_tile<128>(sm.bufS, Lg + o, nullptr, ld, nr, cs(i1), bt);
       }
       bg_sync();
       if (has_r1 && j >= 1) {
@@ -582,16 +589,14 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       DagTask run = hb;
       while (!have) {
         // ---- 1. the row task in progress: its next sub-step ----
+        // The links of a row's dependency chain follow each other within microseconds and the chain CTA cannot run
+        // faster than the rows below it, so the holder of a row task polls and takes no new work -- unless the only
+        // thing its next sub-step waits for is bulk progress (the merge of the bulk buffer): then it helps with that.
+        int rstate = 0;
         if (rt_valid) {
           const DagTask sub = row_sub(rt, rt_c);
-          if (dag_ready(sub, P.upd, P.fb, P.nblk, lane)) { run = sub; have = 2; break; }
-          // A sub-worker holds ONE item, a row task or a bulk ticket, never both: the links of a row's dependency chain
-          // follow each other within microseconds and the chain CTA cannot run faster than the rows below it, so a
-          // holder of a row task only polls (a 40 us bulk task in between would be added to the row's period).
-          // Deadlock freedom: row tasks wait for earlier row tasks (claimed in order, each polled by its holder), the
-          // chain and bulk updates; bulk tickets are taken in an order in which every predecessor on the same tile is
-          // taken first, by sub-workers that hold nothing else; and at most active_cap sub-workers hold row tasks.
-          continue;
+          rstate = dag_state(sub, P.upd, P.fb, P.nblk, lane);
+          if (rstate == 0) { run = sub; have = 2; break; }
         } else if (!hb_valid && seg_lo < P.nblk) {
           // ---- 2. claim a row task of the lowest released column that still has unclaimed ones ----
           const int pos = ld_acquire(P.chain_pos);
@@ -618,16 +623,18 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (rt_valid) continue;
           }
         }
-        // ---- 3. the bulk slot ----
+        // ---- 3. the bulk slot: a ticket already held runs as soon as it is ready (whatever else this sub-worker holds:
+        //      nobody ever sits on a ready task); a new ticket is taken only by a sub-worker without a row task, or one
+        //      whose row task waits for bulk progress ----
         if (hb_valid && dag_ready(hb, P.upd, P.fb, P.nblk, lane)) { run = hb; hb_valid = false; have = 1; break; }
-        if (!hb_valid && !b_done) {
+        if (!hb_valid && !b_done && (!rt_valid || rstate == 2)) {
           // Bulk queues: one per source outer block m, each ordered by target column c; a queue is released when the
           // chain has published the last column of its block.  The bulk updates of one block are applied in source
-          // order, one after the other (~30 us each), and must all be in when the block is merged, i.e. when the chain
-          // reaches column block q = c / 4: the head with the smallest 5 q + 3 m goes first (earliest deadline once the
-          // chunks still to follow on the same block are counted at ~1.5 chain steps each).  Smallest c alone leaves
-          // all chunks of a block to the last moment, in sequence; smallest m alone lets a backlog of far-right updates
-          // of old blocks delay the columns the chain is about to reach.  Lane m inspects queue m.
+          // order, one after the other, and must all be in when the block is merged, i.e. when the chain reaches
+          // column c - 1: the head with the smallest (c - 1) - (number of chunks still to follow on the same block)
+          // goes first (earliest deadline, one chain step per later chunk).  Smallest c alone leaves all chunks of a
+          // block to the last moment, in sequence; smallest m alone lets a backlog of far-right updates of old blocks
+          // delay the columns the chain is about to reach.  Lane m inspects queue m.
           const int pos = ld_acquire(P.chain_pos);
           unsigned key = 0xffffffffu;
           bool exhausted = true;
@@ -636,8 +643,10 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int h = ld_relaxed(P.bhead + lane);
             if (h < size) {
               exhausted = false;
-              if (pos >= min(OUTER * (lane + 1), P.nblk))
-                key = ((unsigned)(5 * (P.btasks[base + h].cb / OUTER) + 3 * lane) << 8) | (unsigned)lane;
+              if (pos >= min(OUTER * (lane + 1), P.nblk)) {
+                const int c = P.btasks[base + h].cb;
+                key = ((unsigned)(2 * c - 2 * (c / OUTER - 2 - lane)) << 8) | (unsigned)lane;
+              }
             }
           }
           const unsigned best = __reduce_min_sync(0xffffffffu, key);

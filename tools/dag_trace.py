@@ -81,7 +81,7 @@ if bg_end.any():
 narrow = ((ids >> 15) & 1) == 1
 for name, sel in (("panel", (typ == 0) & ~narrow), ("panel 64-row", (typ == 0) & narrow),
                   ("update K=64", (typ == 1) & (nk == 1) & ~narrow), ("update K=64 64-row", (typ == 1) & (nk == 1) & narrow),
-                  ("update K=256", (typ == 1) & (nk > 1))):
+                  ("update bulk (K=64*nk)", (typ == 1) & (nk > 1))):
     if sel.any():
         dd = (t1s[sel] - t0s[sel]) / 1e3
         print("%-13s %6d tasks, mean %.2f us, p50 %.2f, p95 %.2f, total %.1f ms-SMhalf" % (name, sel.sum(), dd.mean(), np.median(dd),
