@@ -59,19 +59,21 @@ struct PhaseTimer {
   std::vector<Rec> recs;
   cudaStream_t st;
   explicit PhaseTimer(cudaStream_t s) : st(s) {}
-  void begin(int phase) {
+  cudaStream_t cur = nullptr;
+  void begin(int phase, cudaStream_t on) {
     if (!g_profile) return;
     Rec r;
     r.phase = phase;
+    cur = on;
     cudaEventCreate(&r.e0);
     cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, st);
+    cudaEventRecord(r.e0, on);
     r.h0 = r.h1 = now_ms();
     recs.push_back(r);
   }
   void end() {
     if (!g_profile || recs.empty()) return;
-    cudaEventRecord(recs.back().e1, st);
+    cudaEventRecord(recs.back().e1, cur);
     recs.back().h1 = now_ms();
   }
   void collect() {   // call after the stream has been synchronised
@@ -105,6 +107,8 @@ struct DeviceCtx {
   void* io2 = nullptr;         // grow-only gather / R-layout buffers on the root device
   size_t io2_bytes = 0;
   Lookahead la;                // second stream + events of the single-matrix Cholesky's lookahead schedule
+  cudaStream_t prep = nullptr; // high-priority side stream of the gradient pipeline (factorisations of the next batch)
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
 };
 static DeviceCtx g_ctx[64];
 static std::mutex g_ctx_mu;
@@ -256,6 +260,11 @@ static int ncomp_of(int type) { return type == SPW_COV_MATERN1 ? 2 : 5; }
 static long long pad_ld(long long n) { return round_up_ll(n, 16); }
 
 // ---- the per-shard spatial_gradient driver (device pointers) -------------------------------------------
+// Batches of B samples go through two stages: "prep" (covariance assembly, batched Cholesky, triangular inverse,
+// v = Linv z -- many short, latency-bound kernels) and "main" (cross-covariances + the fused TRMM / Gram / draw kernel).
+// Optionally (SPW_OVERLAP=1) the stages run on two streams with double-buffered factors, so that the prep of batch k+1
+// runs while the main kernel of batch k owns the SMs; see the note at `overlap` below for why this is not the default.
+// Status words live in one array for the whole shard and are read once at the end: no host sync per batch.
 static int gradient_shard(int type, int n, const double* cx, const double* cy, int G, const double* gx,
                           const double* gy, int S, const double* phi, const double* sig2, const double* z, int ldz,
                           const double* eps, double* out_draws, double* out_mean, double* out_var, int* info,
@@ -266,12 +275,19 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   if (S == 0) return SPW_OK;
   DeviceCtx* ctx;
   SPW_TRY(get_ctx(&ctx));
+  // Measured on B200 (C5, 64 samples per call): 2506 ms with the two-stream pipeline against 2515 ms without -- the
+  // main kernel's CTAs run 8.5 ms each and retire in waves, so a dependent chain of ~600 short prep kernels only finds
+  // free SMs once per wave; and since the fused kernel already keeps the FP64 pipe 96 % busy, the most an overlap can
+  // recover is the idle share of the factorisations (< 3 % of a step).  Off by default (SPW_OVERLAP=1 enables it).
+  static const bool overlap = getenv("SPW_OVERLAP") && getenv("SPW_OVERLAP")[0] == '1';
+  const int nset = overlap ? 2 : 1;
   const int c = ncomp_of(type);
   const long long ld = pad_ld(n);
   const int nblk = ceil_div(n, NB);
   // workspace sizing: batch B samples, grid chunk gc
   const size_t mat = (size_t)n * ld * sizeof(double);
-  const size_t per_sample_fixed = 2 * mat + (size_t)ld * sizeof(double) + (size_t)nblk * NB * NB * sizeof(double) + 64;
+  const size_t per_sample_fixed =
+      nset * (2 * mat + (size_t)ld * sizeof(double) + (size_t)nblk * NB * NB * sizeof(double) + 64);
   const size_t at_per_g = (size_t)c * ld * sizeof(double);
   // the (B, gc) decision is cached per problem shape so that repeated calls skip cudaMemGetInfo
   struct ShapeKey { int dev, type, n, G, S; size_t limit; int B, gc; };
@@ -280,9 +296,10 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
   SPW_CUDA(cudaGetDevice(&cur_dev));
   // reuse only on the same device and only while the cached choice still fits the workspace this context already owns
   // (otherwise the budget is consulted again: other allocations may have grown since)
+  const size_t status_bytes = sizeof(int) * 2 * (size_t)S + 256;
   const bool reuse = (last.dev == cur_dev && last.type == type && last.n == n && last.G == G && last.S == S &&
                       last.limit == (size_t)g_ws_limit &&
-                      ctx->ws_bytes >= (per_sample_fixed + at_per_g * (size_t)last.gc) * (size_t)last.B + 4096);
+                      ctx->ws_bytes >= (per_sample_fixed + at_per_g * (size_t)last.gc) * (size_t)last.B + status_bytes + 4096);
   const size_t budget = reuse ? 0 : workspace_budget();
   int gc = std::min(G, 65535);
   int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / (per_sample_fixed + at_per_g * gc));
@@ -301,51 +318,82 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
     gc = gc / 16 * 16;
     if (gc < 16) { set_error("spw_gradient: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
   }
+  // at least two batches, so that the second one's factorisations hide behind the first one's main kernel
+  if (!reuse && overlap && S >= 8 && B > (S + 1) / 2) B = (S + 1) / 2;
   last = ShapeKey{cur_dev, type, n, G, S, (size_t)g_ws_limit, B, gc};
   const LinalgPlan* plan;
   SPW_TRY(get_plan(*ctx, n, 0, B < 4 ? 1 : 0, &plan));
-  const size_t total = (per_sample_fixed + at_per_g * gc) * B + 4096;
+  const size_t total = (per_sample_fixed + at_per_g * gc) * B + status_bytes + 4096;
   void* wsp;
   SPW_TRY(get_workspace(*ctx, total, &wsp));
   Carver cv(wsp);
-  double* Lb = cv.take<double>((size_t)B * n * ld);
-  double* Li = cv.take<double>((size_t)B * n * ld);
+  double *Lb[2], *Li[2], *vb[2], *dinv[2];
+  for (int i = 0; i < nset; ++i) {
+    Lb[i] = cv.take<double>((size_t)B * n * ld);
+    Li[i] = cv.take<double>((size_t)B * n * ld);
+    vb[i] = cv.take<double>((size_t)B * ld);
+    dinv[i] = cv.take<double>((size_t)B * nblk * NB * NB);
+  }
   double* At = cv.take<double>((size_t)B * gc * c * ld);
-  double* vb = cv.take<double>((size_t)B * ld);
-  double* dinv = cv.take<double>((size_t)B * nblk * NB * NB);
-  int* status = cv.take<int>((size_t)2 * B);
-  std::vector<int> h_status(2 * (size_t)B);
-  MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld}, AT{At, ld, (long long)gc * c * ld};
-
+  int* status = cv.take<int>(2 * (size_t)S);      // [0, S): chol(K); [S, 2S): the 5 x 5 factorisations
+  MatView AT{At, ld, (long long)gc * c * ld};
+  // side stream and events of the two-stage pipeline
+  cudaStream_t ps = st;
+  if (overlap) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!ctx->prep) {
+      int lo = 0, hi = 0;
+      SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SPW_CUDA(cudaStreamCreateWithPriority(&ctx->prep, cudaStreamNonBlocking, hi));
+      for (int i = 0; i < 2; ++i) {
+        SPW_CUDA(cudaEventCreateWithFlags(&ctx->ev_prep[i], cudaEventDisableTiming));
+        SPW_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+      }
+      SPW_CUDA(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    }
+    ps = ctx->prep;
+  }
+  SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 2 * (size_t)S, st));
+  if (overlap) {
+    SPW_CUDA(cudaEventRecord(ctx->ev_start, st));          // the side stream starts after the caller's earlier work
+    SPW_CUDA(cudaStreamWaitEvent(ps, ctx->ev_start, 0));
+  }
   PhaseTimer pt(st);
   const char* env_main = getenv("SPW_MAIN");
   const bool use_tma = !(env_main && env_main[0] == '0');
-  for (int s0 = 0; s0 < S; s0 += B) {
-    const int nb = std::min(B, S - s0);
-    SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 2 * B, st));
-    // K = cov(phi_s, sig2 = 1), no nugget            R/spatial_gradient.R:215,264,303
-    pt.begin(PH_COV);
-    SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, nullptr, 1, L, nb, 1, st));
+  int k = 0;
+  for (int s0 = 0; s0 < S; s0 += B, ++k) {
+    const int nb = std::min(B, S - s0), set = overlap ? (k & 1) : 0;
+    MatView L{Lb[set], ld, (long long)n * ld}, Linv{Li[set], ld, (long long)n * ld};
+    // ---- prep: K = cov(phi_s, sig2 = 1), no nugget; chol(K); its triangular inverse; v = Linv z
+    //      R/spatial_gradient.R:215-216,264-265,303-304 ----
+    if (overlap && k >= 2) SPW_CUDA(cudaStreamWaitEvent(ps, ctx->ev_free[set], 0));   // main of batch k-2 is done with this set
+    pt.begin(PH_COV, ps);
+    SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, nullptr, 1, L, nb, 1, ps));
     pt.end();
-    // chol(K) and its triangular inverse            R/spatial_gradient.R:216,265,304
-    pt.begin(PH_POTRF);
-    SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status, st));
+    pt.begin(PH_POTRF, ps);
+    SPW_TRY(potrf_batched(*plan, L, dinv[set], &Linv, nb, status + s0, ps));
     pt.end();
-    pt.begin(PH_TRTRI);
-    SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    pt.begin(PH_TRTRI, ps);
+    SPW_TRY(trtri_batched(*plan, L, Linv, nb, ps));
     pt.end();
-    pt.begin(PH_TRMV);
-    SPW_TRY(trmv_lower_batched(n, Linv, z + (long long)s0 * ldz, ldz, vb, ld, nb, st));
+    pt.begin(PH_TRMV, ps);
+    SPW_TRY(trmv_lower_batched(n, Linv, z + (long long)s0 * ldz, ldz, vb[set], ld, nb, ps));
     pt.end();
+    if (overlap) {
+      SPW_CUDA(cudaEventRecord(ctx->ev_prep[set], ps));
+      SPW_CUDA(cudaStreamWaitEvent(st, ctx->ev_prep[set], 0));
+    }
+    // ---- main: cross-covariances and the fused kernel for every grid chunk ----
     for (int g0 = 0; g0 < G; g0 += gc) {
       const int ng = std::min(gc, G - g0);
-      pt.begin(PH_CROSS);
+      pt.begin(PH_CROSS, st);
       SPW_TRY(cross_cov_batched(type, n, cx, cy, g0, ng, gx, gy, phi + s0, AT, nb, st));
       pt.end();
       GradParams P;
       P.linv = Linv;
       P.at = AT;
-      P.v = vb;
+      P.v = vb[set];
       P.ldv = ld;
       P.phi = phi + s0;
       P.sig2 = sig2 + s0;
@@ -353,13 +401,13 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
       P.out_draws = out_draws;
       P.out_mean = out_mean;
       P.out_var = out_var;
-      P.status = status + B;
+      P.status = status + S + s0;
       P.n = n;
       P.g_begin = g0;
       P.g_count = ng;
       P.g_total = G;
       P.s_begin = s0;
-      pt.begin(PH_MAIN);
+      pt.begin(PH_MAIN, st);
       if (use_tma) SPW_TRY(gradient_tma_launch(type, P, nb, st));
       else SPW_TRY(gradient_main_launch(type, P, nb, st));
       pt.end();
@@ -368,20 +416,22 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
         g_main_flops += (double)nb * ng * ((double)c * n * ((double)n + 1.0) + (double)(c * (c + 1) + 2 * c) * n);
       }
     }
-    SPW_CUDA(cudaMemcpyAsync(h_status.data(), status, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost, st));
-    SPW_CUDA(cudaStreamSynchronize(st));
-    pt.collect();
-    for (int b = 0; b < nb; ++b) {
-      if (h_status[b]) {
-        if (info) { info[0] = s0 + b + 1; info[1] = h_status[b]; info[2] = 1; }
-        set_error("spatial_gradient: sample %d: the leading minor of order %d of K is not positive", s0 + b + 1, h_status[b]);
-        return SPW_ERR_NOT_PD;
-      }
-      if (h_status[B + b]) {
-        if (info) { info[0] = s0 + b + 1; info[1] = h_status[B + b]; info[2] = 2; }
-        set_error("spatial_gradient: sample %d, grid point %d: var.grad is not positive definite", s0 + b + 1, h_status[B + b]);
-        return SPW_ERR_NOT_PD;
-      }
+    if (overlap) SPW_CUDA(cudaEventRecord(ctx->ev_free[set], st));
+  }
+  std::vector<int> h_status(2 * (size_t)S);
+  SPW_CUDA(cudaMemcpyAsync(h_status.data(), status, sizeof(int) * 2 * (size_t)S, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  pt.collect();
+  for (int s = 0; s < S; ++s) {
+    if (h_status[s]) {
+      if (info) { info[0] = s + 1; info[1] = h_status[s]; info[2] = 1; }
+      set_error("spatial_gradient: sample %d: the leading minor of order %d of K is not positive", s + 1, h_status[s]);
+      return SPW_ERR_NOT_PD;
+    }
+    if (h_status[S + s]) {
+      if (info) { info[0] = s + 1; info[1] = h_status[S + s]; info[2] = 2; }
+      set_error("spatial_gradient: sample %d, grid point %d: var.grad is not positive definite", s + 1, h_status[S + s]);
+      return SPW_ERR_NOT_PD;
     }
   }
   return SPW_OK;
@@ -683,6 +733,15 @@ int spw_shutdown(void) {
     c.stream = nullptr;
     if (c.la.bulk) cudaStreamDestroy(c.la.bulk);
     c.la.bulk = nullptr;
+    if (c.prep) {
+      cudaStreamDestroy(c.prep);
+      c.prep = nullptr;
+      for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c.ev_prep[i]);
+        cudaEventDestroy(c.ev_free[i]);
+      }
+      cudaEventDestroy(c.ev_start);
+    }
     for (auto e : c.la.ev_chain) cudaEventDestroy(e);
     for (auto e : c.la.ev_bulk) cudaEventDestroy(e);
     for (auto e : c.la.ev_aux) cudaEventDestroy(e);
