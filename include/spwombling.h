@@ -147,6 +147,19 @@ int spw_gradient_shard_dev(int type, int n, const double* coords_dev, int g, con
 int spw_spsample_run(int type, int n, const double* coords, int S, const double* phi, const double* sig2,
                      const double* tau2, const double* w, const double* eps, double* out_z, int* bad, int* info);
 
+/* bayes_cwomb(type = "rectilinear", approx = NULL) -- R/spatial_wombling.R:159-244
+ * (matern2) and :308-393 (gaussian), kernels Gamma.* / K.* :464-711.  The branch does not run upstream as written
+ * (`ntimes <- 1:length(model$phis)`); the semantics implemented are ntimes = S = length(model$phi), everything else
+ * literally (see oracle/wombling.py and DESIGN.md).  type: SPW_COV_GAUSSIAN or SPW_COV_MATERN2 (the matern1 kernels
+ * divide 0 by 0 upstream).  curve: (nseg + 1) x 2 column-major polyline; rule_len: rule.len; z: S x n column-major;
+ * eps [S][nseg][2]: the two rnorm() variates mvrnorm consumes per (sample, segment).
+ * out_w [2][S][nseg] = womb1.mcmc, womb2.mcmc (each nseg x S column-major); optional out_mean [S][nseg][2] (mean.womb)
+ * and out_var [S][nseg][4] (var.womb, row-major 2 x 2).  SPW_ERR_NOT_PD with info = {sample, minor, 1} when
+ * chol(Sig.Z) fails, {sample, segment, 3} when mvrnorm's "'Sigma' is not positive definite" test fails. */
+int spw_wombling_rect_run(int type, int n, const double* coords, int nseg, const double* curve, int rule_len, int S,
+                          const double* phi, const double* sig2, const double* z, const double* eps, double* out_w,
+                          double* out_mean, double* out_var, int* info);
+
 /* spw_hpd_summary: batch medians, median of batch medians and coda::HPDinterval over the batch
  *   medians -- R/spatial_gradient.R:391-419 (:353-358 for matern1).  draws [S x g] column-major,
  *   out [g x 3] column-major (estimate, lower, upper), unrounded. */

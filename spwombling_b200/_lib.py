@@ -43,6 +43,8 @@ SIGNATURES = {
     "spw_gradient_shard_dev": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
                                        c_vp, c_vp, c_vp, c_vp]),
     "spw_spsample_run": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "spw_wombling_rect_run": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp]),
     "spw_hpd_summary": (c_int, [c_int, c_int, c_int, c_dbl, c_vp, c_vp]),
     "spw_hpd_summary_dev": (c_int, [c_int, c_int, c_int, c_int, c_dbl, c_vp, c_vp, c_vp]),
     "spw_draws_to_r_layout_dev": (c_int, [c_int, c_int, c_int, c_vp, c_vp, c_vp]),

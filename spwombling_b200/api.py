@@ -275,15 +275,26 @@ def spsample(y=None, X=None, coords=None, phi=None, sig2=None, tau2=None, cov_ty
 
 
 def bayes_cwomb(coords=None, model=None, cov_type=None, nbatch=None, curve=None, type="riemann.sum", approx=None,
-                verbose=True, rule_len=10, eps=None, rng=None, ngpu=1, rounded=True):
+                verbose=True, rule_len=10, eps=None, rng=None, ngpu=1, rounded=True, return_moments=False):
     """Curvilinear wombling measures along a polyline -- R/spatial_wombling.R:28-36, ``type = "riemann.sum"`` branches
     (:114-157 matern1, :245-306 matern2, :394-455 gaussian): ``spatial_gradient`` at the curve vertices (GPU path),
     projection on each segment's unit normal, batch medians + HPD per segment, length-weighted measures.
     Returns the reference's list as a dict: ``tval, uval, womb1.mcmc, [womb2.mcmc], womb.grad.inf, [womb.curv.inf],
-    womb.measure.inf``.  ``type = "rectilinear"`` is not provided: that branch is broken upstream (``model$phis``,
-    ``1:ntimes`` on a vector -- SURVEY section 8f rank 3)."""
+    womb.measure.inf``.
+
+    ``type = "rectilinear"`` (:159-244 matern2, :308-393 gaussian; ``approx`` must be None like the only branch the
+    reference implements): the line-integral measures by quadrature over ``rule_len`` nodes -- cross-covariances
+    ``Gamma.*``, the double quadrature of ``K.*``, the ``K^-1`` sandwich and the ``mvrnorm`` draw all on the GPU
+    (``spw_wombling_rect_run``).  That branch does not run upstream as written (``model$phis``, ``1:ntimes`` on a
+    vector); the semantics here are ntimes = length(model$phi), everything else literally, see oracle/wombling.py.
+    matern1 is refused: its ``K.11.m1`` divides 0 by 0, so the reference could only stop in ``eigen``.  ``eps``
+    [S, nseg, 2] injects the variates of ``mvrnorm`` (``return_moments`` adds ``mean.womb`` / ``var.womb``)."""
+    if type == "rectilinear":
+        if approx is not None:
+            raise NotImplementedError("bayes_cwomb: only approx = NULL is implemented upstream (R/spatial_wombling.R:47,160,309)")
+        return _bayes_cwomb_rectilinear(coords, model, cov_type, nbatch, curve, rule_len, eps, rng, return_moments)
     if type != "riemann.sum":
-        raise NotImplementedError("bayes_cwomb(type='rectilinear') is broken upstream and not ported (SURVEY 8f rank 3)")
+        raise ValueError("type must be 'rectilinear' or 'riemann.sum'")
     curve = np.asarray(curve, dtype=np.float64)
     d = curve[1:] - curve[:-1]
     tval = np.sqrt((d ** 2).sum(axis=1))                                   # R/spatial_wombling.R:42
@@ -324,6 +335,50 @@ def bayes_cwomb(coords=None, model=None, cov_type=None, nbatch=None, curve=None,
     else:
         out["womb.grad.inf"] = grad_inf
     out["womb.measure.inf"] = np.stack(rows)
+    return out
+
+
+def _bayes_cwomb_rectilinear(coords, model, cov_type, nbatch, curve, rule_len, eps, rng, return_moments):
+    if cov_type == "matern1":
+        raise NotImplementedError("bayes_cwomb(type='rectilinear', cov.type='matern1'): K.11.m1 divides 0 by 0 on the node "
+                                  "pairs with t1 = t2 (R/spatial_wombling.R:605-607), so the reference stops in mvrnorm")
+    code = _code(cov_type)
+    coords = f64(coords, "F")
+    curve = f64(curve, "F")
+    n, nseg = coords.shape[0], curve.shape[0] - 1
+    phi = f64(np.asarray(model["phi"]).reshape(-1), "C")
+    sig2 = f64(np.asarray(model["sig2"]).reshape(-1), "C")
+    S = phi.shape[0]
+    z = f64(np.asarray(model["z"]).reshape(S, n), "F")
+    if eps is None:
+        rng = np.random.default_rng() if rng is None else rng
+        eps = rng.standard_normal((S, nseg, 2))
+    eps = f64(np.asarray(eps).reshape(S, nseg, 2), "C")
+    w = np.empty((2, S, nseg), dtype=np.float64)
+    mean = np.empty((S, nseg, 2), dtype=np.float64) if return_moments else None
+    var = np.empty((S, nseg, 2, 2), dtype=np.float64) if return_moments else None
+    info = np.zeros(4, dtype=np.int32)
+    rc = load().spw_wombling_rect_run(code, n, ptr(coords), nseg, ptr(curve), int(rule_len), S, ptr(phi), ptr(sig2), ptr(z),
+                                      ptr(eps), ptr(w), ptr(mean), ptr(var), ptr(info))
+    check(rc, info)
+    d = np.asarray(curve)[1:] - np.asarray(curve)[:-1]
+    tval = np.sqrt((d ** 2).sum(axis=1))                                   # R/spatial_wombling.R:42-43
+    uval = d / tval[:, None]
+    out = {"tval": tval, "uval": uval, "womb1.mcmc": w[0].T, "womb2.mcmc": w[1].T}      # nseg x S
+
+    def inf(ws):                                                           # :213-226 / :228-230
+        est = hpd_summary(ws, nbatch)                                      # batch medians, their median and HPD
+        sig = np.where((est[:, 1] > 0) & (est[:, 2] > 0), 1.0, np.where((est[:, 1] < 0) & (est[:, 2] < 0), -1.0, 0.0))
+        lab = np.ceil(np.arange(1, S + 1) / (S / nbatch)).astype(int)      # the split(...) rule of :212
+        bm = np.stack([np.median(ws[lab == b], axis=0) for b in np.unique(lab)])
+        tot = bm.sum(axis=1) / tval.sum()
+        h = hpd_summary(tot[:, None], tot.shape[0])[0]                     # HPD over the per-batch totals
+        return np.column_stack([est, sig]), np.array([est[:, 0].sum() / tval.sum(), np.median(tot), h[1], h[2]])
+    g_inf, g_row = inf(w[0])
+    c_inf, c_row = inf(w[1])
+    out.update({"womb.grad.inf": g_inf, "womb.curv.inf": c_inf, "womb.measure.inf": np.stack([g_row, c_row])})
+    if return_moments:
+        out["mean.womb"], out["var.womb"] = mean, var
     return out
 
 

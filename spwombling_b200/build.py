@@ -10,10 +10,12 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libspwombling.so")
-SOURCES = ["api.cu", "cov.cu", "linalg.cu", "potrf_dag.cu", "gradient.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
+SOURCES = ["api.cu", "cov.cu", "linalg.cu", "potrf_dag.cu", "wombling.cu", "gradient.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
 # cov.cu is compiled without FMA contraction: its elementwise formulas then round exactly like the reference's
 # R arithmetic (and K[i][j] == K[j][i] bit for bit, whichever thread computes it)
-EXTRA_FLAGS = {"cov.cu": ["-fmad=false"]}
+# wombling.cu likewise: its double quadrature relies on t2 - t1 being exactly zero on the diagonal node pairs (the
+# reference switches to a zero-lag formula there); an FMA-contracted a2 * tval - a1 * tval would leave a rounding residue
+EXTRA_FLAGS = {"cov.cu": ["-fmad=false"], "wombling.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 

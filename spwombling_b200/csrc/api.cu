@@ -22,6 +22,7 @@
 #include "potrf_dag.cuh"
 #include "summary.cuh"
 #include "tma.cuh"
+#include "wombling.cuh"
 
 namespace spw {
 
@@ -1162,6 +1163,117 @@ int spw_gradient_run(int type, int n, const double* coords, int g, const double*
             "gather %.1f (%s) + summary %.1f + draws to R layout and D2H %.1f\n", S, g, n, ngpu, t_end - t_begin,
             t_compute - t_begin, ts, t_gather - t_compute, ngpu == 1 ? "none" : (g_last_gather_nccl == 1 ? "nccl" : "peer copies"),
             t_summary - t_gather, t_end - t_summary);
+  }
+  return SPW_OK;
+}
+
+// bayes_cwomb(type = "rectilinear"): host buffers in, the two wombling measures per (segment, sample) out.
+int spw_wombling_rect_run(int type, int n, const double* coords, int nseg, const double* curve, int rule_len, int S,
+                          const double* phi, const double* sig2, const double* z, const double* eps, double* out_w,
+                          double* out_mean, double* out_var, int* info) {
+  if ((type != SPW_COV_GAUSSIAN && type != SPW_COV_MATERN2) || n < 1 || nseg < 1 || rule_len < 2 || S < 0 || !coords ||
+      !curve || (S && (!phi || !sig2 || !z || !eps || !out_w))) {
+    set_error("spw_wombling_rect_run: bad arguments (cov type must be gaussian or matern2: the matern1 kernels of the "
+              "reference divide 0 by 0)");
+    return SPW_ERR_ARG;
+  }
+  if (info) info[0] = info[1] = info[2] = info[3] = 0;
+  if (S == 0) return SPW_OK;
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const long long ld = pad_ld(n);
+  const int nblk = ceil_div(n, NB);
+  const size_t per_sample = 2 * (size_t)n * ld * sizeof(double) + (size_t)ld * sizeof(double) +
+                            (size_t)nblk * NB * NB * sizeof(double) + (size_t)nseg * 2 * ld * sizeof(double) + 64;
+  const size_t budget = workspace_budget();
+  int B = (int)std::min<size_t>((size_t)std::min(S, 1024), budget / per_sample);
+  if (B < 1) { set_error("spw_wombling_rect_run: workspace too small (n = %d)", n); return SPW_ERR_ARG; }
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, 0, B < 4 ? 1 : 0, &plan));
+  void* wsp;
+  SPW_TRY(get_workspace(*ctx, per_sample * B + 4096, &wsp));
+  Carver cv(wsp);
+  double* Lb = cv.take<double>((size_t)B * n * ld);
+  double* Li = cv.take<double>((size_t)B * n * ld);
+  double* At = cv.take<double>((size_t)B * nseg * 2 * ld);
+  double* vb = cv.take<double>((size_t)B * ld);
+  double* dinv = cv.take<double>((size_t)B * nblk * NB * NB);
+  // inputs / outputs of the whole call in the context's staging buffer
+  const size_t n_units = (size_t)S * nseg;
+  size_t need = 4096 + sizeof(double) * (2 * (size_t)n + 2 * ((size_t)nseg + 1) + 2 * (size_t)S + (size_t)S * n + (size_t)S * ld +
+                                         n_units * (2 + 5 + 2 + 2 + 4)) + sizeof(int) * 3 * (size_t)S + 16 * 256;
+  SPW_TRY(grow_buffer(&ctx->io, &ctx->io_bytes, need));
+  Carver io(ctx->io);
+  double* dc = io.take<double>(2 * (size_t)n);
+  double* dcurve = io.take<double>(2 * ((size_t)nseg + 1));
+  double* dphi = io.take<double>(S);
+  double* dsig = io.take<double>(S);
+  double* dzr = io.take<double>((size_t)S * n);
+  double* dz = io.take<double>((size_t)S * ld);
+  double* deps = io.take<double>(n_units * 2);
+  double* dgram = io.take<double>(n_units * 5);
+  double* dw = io.take<double>(n_units * 2);
+  double* dmean = io.take<double>(n_units * 2);
+  double* dvar = io.take<double>(n_units * 4);
+  int* status = io.take<int>(3 * (size_t)S);            // chol(K) | the fused kernel's own (unused) 2 x 2 | mvrnorm
+  SPW_CUDA(cudaMemcpyAsync(dc, coords, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dcurve, curve, sizeof(double) * 2 * (nseg + 1), cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dphi, phi, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dsig, sig2, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemcpyAsync(dzr, z, sizeof(double) * (size_t)S * n, cudaMemcpyHostToDevice, st));      // S x n column-major
+  SPW_TRY(transpose_batched(n, S, dzr, S, 0, dz, ld, 0, 1, st));
+  SPW_CUDA(cudaMemcpyAsync(deps, eps, sizeof(double) * n_units * 2, cudaMemcpyHostToDevice, st));
+  SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 3 * (size_t)S, st));
+  MatView L{Lb, ld, (long long)n * ld}, Linv{Li, ld, (long long)n * ld}, AT{At, ld, (long long)nseg * 2 * ld};
+  for (int s0 = 0; s0 < S; s0 += B) {
+    const int nb = std::min(B, S - s0);
+    // K = cov(phi, sig2 = 1): the reference's sig2 * K enters as 1 / sig2 factors in womb_finish_kernel
+    SPW_TRY(cov_assemble_batched(type, n, dc, dc + n, dphi + s0, nullptr, nullptr, 1, L, nb, 1, st));
+    SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status + s0, st));
+    SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    SPW_TRY(trmv_lower_batched(n, Linv, dz + (long long)s0 * ld, ld, vb, ld, nb, st));
+    SPW_TRY(womb_gamma_batched(type, n, dc, dc + n, dcurve, nseg, rule_len, dphi + s0, AT, nb, st));
+    GradParams P;
+    P.linv = Linv;
+    P.at = AT;
+    P.v = vb;
+    P.ldv = ld;
+    P.phi = dphi + s0;
+    P.sig2 = dsig + s0;
+    P.eps = nullptr;
+    P.out_draws = nullptr;
+    P.out_mean = nullptr;
+    P.out_var = nullptr;
+    P.out_gram = dgram;
+    P.status = status + S + s0;
+    P.n = n;
+    P.g_begin = 0;
+    P.g_count = nseg;
+    P.g_total = nseg;
+    P.s_begin = s0;
+    // two components per segment: the fused kernel in its two-component instantiation returns M = G K^-1 G' and G K^-1 z
+    SPW_TRY(gradient_tma_launch(SPW_COV_MATERN1, P, nb, st));
+    SPW_TRY(womb_finish_batched(type, nb, s0, S, nseg, rule_len, dcurve, dphi + s0, dsig + s0, dgram, deps, dw, dmean, dvar,
+                                status + 2 * (size_t)S + s0, st));
+  }
+  std::vector<int> hs(3 * (size_t)S);
+  SPW_CUDA(cudaMemcpyAsync(hs.data(), status, sizeof(int) * 3 * (size_t)S, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaMemcpyAsync(out_w, dw, sizeof(double) * n_units * 2, cudaMemcpyDeviceToHost, st));
+  if (out_mean) SPW_CUDA(cudaMemcpyAsync(out_mean, dmean, sizeof(double) * n_units * 2, cudaMemcpyDeviceToHost, st));
+  if (out_var) SPW_CUDA(cudaMemcpyAsync(out_var, dvar, sizeof(double) * n_units * 4, cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < S; ++s) {
+    if (hs[s]) {
+      if (info) { info[0] = s + 1; info[1] = hs[s]; info[2] = 1; }
+      set_error("bayes_cwomb: sample %d: the leading minor of order %d of Sig.Z is not positive", s + 1, hs[s]);
+      return SPW_ERR_NOT_PD;
+    }
+    if (hs[2 * (size_t)S + s]) {
+      if (info) { info[0] = s + 1; info[1] = hs[2 * (size_t)S + s]; info[2] = 3; }
+      set_error("bayes_cwomb: sample %d, segment %d: 'Sigma' is not positive definite (mvrnorm)", s + 1, hs[2 * (size_t)S + s]);
+      return SPW_ERR_NOT_PD;
+    }
   }
   return SPW_OK;
 }

@@ -81,16 +81,20 @@ __host__ __device__ __forceinline__ long long round_up_ll(long long a, long long
 
 // ---- covariance functions of the reference (R/cov_gaussian.R:14, R/cov_matern1.R:14, R/cov_matern2.R:14)
 // rho(d) with sig2 = 1; the gaussian kernel squares the (square-rooted) distance as the reference does.
+// Every product and sum is an explicitly rounded operation (no FMA contraction whatever the flags of the translation
+// unit), so the assembled matrix, the single-CTA hlm chain and spw_cov see bit-identical covariances and
+// K[i][j] == K[j][i].
 template <int TYPE>
 __device__ __forceinline__ double cov_rho(double phi, double d) {
   if constexpr (TYPE == 0) {
-    return exp(-phi * (d * d));
+    return exp(-__dmul_rn(phi, __dmul_rn(d, d)));
   } else if constexpr (TYPE == 1) {
-    const double ad = phi * 1.7320508075688772 * d;   // phi * sqrt(3) * Delta
-    return (1.0 + ad) * exp(-ad);
+    const double ad = __dmul_rn(__dmul_rn(phi, 1.7320508075688772), d);   // phi * sqrt(3) * Delta
+    return __dmul_rn(__dadd_rn(1.0, ad), exp(-ad));
   } else {
-    const double ad = phi * 2.2360679774997898 * d;   // phi * sqrt(5) * Delta
-    return (1.0 + ad + phi * phi * 5.0 * (d * d) / 3.0) * exp(-ad);
+    const double ad = __dmul_rn(__dmul_rn(phi, 2.2360679774997898), d);   // phi * sqrt(5) * Delta
+    const double q = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(phi, phi), 5.0), __dmul_rn(d, d)), 3.0);
+    return __dmul_rn(__dadd_rn(__dadd_rn(1.0, ad), q), exp(-ad));
   }
 }
 

@@ -16,6 +16,8 @@ struct GradParams {
   double* out_draws;       // [S][ncomp][g_total]
   double* out_mean;        // [S][g_total][ncomp] or null
   double* out_var;         // [S][g_total][ncomp*ncomp] (each block column-major) or null
+  double* out_gram = nullptr;   // [S][g_total][ncomp(ncomp+1)/2 + ncomp] or null: the raw sums -- upper triangle of
+                                // M = A K^-1 A^T row by row, then A K^-1 z (TMA kernel only; used by the wombling path)
   int* status;             // [batch]: first grid point (1-based) whose 5x5 chol failed, 0 if none
   int n;
   int g_begin, g_count, g_total;

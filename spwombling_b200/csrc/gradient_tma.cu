@@ -54,6 +54,7 @@ struct TmaParams {
   double* out_draws;
   double* out_mean;
   double* out_var;
+  double* out_gram;
   int* status;
   int n, g_begin, g_count, g_total, s_begin;
 };
@@ -234,6 +235,11 @@ gradient_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int wm = 0; wm < 4; ++wm) s += Ms[(wn * 4 + wm) * C::NIT_W + glw * C::IPG + p];
         m[p] = s;
       }
+      if (P.out_gram) {
+        double* o = P.out_gram + (sidx * P.g_total + gidx) * C::IPG;
+#pragma unroll
+        for (int p = 0; p < C::IPG; ++p) o[p] = m[p];
+      }
       double M[NCOMP][NCOMP], mean[NCOMP];
       {
         int p = 0;
@@ -340,7 +346,7 @@ int gradient_tma_launch(int type, const GradParams& G, int batch, cudaStream_t s
   SPW_TRY(make_tensor_map(&tmB, G.at, G.n, G.g_count * ncomp, batch, T_LDS, bn));
   TmaParams P;
   P.v = G.v; P.ldv = G.ldv; P.phi = G.phi; P.sig2 = G.sig2; P.eps = G.eps;
-  P.out_draws = G.out_draws; P.out_mean = G.out_mean; P.out_var = G.out_var; P.status = G.status;
+  P.out_draws = G.out_draws; P.out_mean = G.out_mean; P.out_var = G.out_var; P.out_gram = G.out_gram; P.status = G.status;
   P.n = G.n; P.g_begin = G.g_begin; P.g_count = G.g_count; P.g_total = G.g_total; P.s_begin = G.s_begin;
   dim3 grid(ceil_div(G.g_count, gpt), batch);
   switch (type) {

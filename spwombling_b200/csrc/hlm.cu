@@ -21,6 +21,7 @@ struct HlmState {
   int oob;              // phi proposal outside [lower.phi, upper.phi]  R/hlmBayes_sp.R:164
   int iter;             // 0-based iteration counter
   int nrep;
+  int fail_iter;        // 1-based iteration whose chol() failed first (0: none); the reference stops there
 };
 
 struct HlmConst {
@@ -56,7 +57,11 @@ struct HlmOut {
   int nrep;
 };
 
-__device__ void hlm_accept(HlmState& s, const HlmConst& c, int p, const double* __restrict__ unif, const HlmOut& o) {
+// failed: chol() of the proposal hit a non-positive pivot (the reference's chol() raises an R error at that point,
+// R/hlmBayes_sp.R:114/140/181).  The proposal is rejected -- a NaN log-ratio must not be "accepted" through
+// fmin(NaN, 0) = 0 -- and the iteration is recorded; the caller returns SPW_ERR_NOT_PD with it.
+__device__ void hlm_accept(HlmState& s, const HlmConst& c, int p, const double* __restrict__ unif, const HlmOut& o,
+                           bool failed) {
   double* out_sig2 = o.sig2; double* out_tau2 = o.tau2; double* out_phi = o.phi; double* out_trgt = o.trgt;
   double* out_accept = o.accept; double* out_tuning = o.tuning;
   const int nrep = o.nrep;
@@ -75,6 +80,10 @@ __device__ void hlm_accept(HlmState& s, const HlmConst& c, int p, const double* 
   else r = -(l - lcur) + lik;                                                                      // :184-185
   double accept_prob = fmin(r, 0.0);
   if (s.oob) accept_prob = -INFINITY;                                                              // :164
+  if (failed || !(r == r)) {
+    accept_prob = -INFINITY;
+    if (s.fail_iter == 0) s.fail_iter = (int)i + 1;
+  }
   if (log(unif[3 * i + p]) < accept_prob) {                                                        // :123, :149, :192
     s.par[p] = exp(l);
     s.quad = s.quad_p;
@@ -110,8 +119,9 @@ __global__ void hlm_propose_kernel(HlmState* S, HlmConst c, int p, const double*
   hlm_propose(*S, c, p, norm);
 }
 
-__global__ void hlm_accept_kernel(HlmState* S, HlmConst c, int p, const double* __restrict__ unif, HlmOut o) {
-  hlm_accept(*S, c, p, unif, o);
+__global__ void hlm_accept_kernel(HlmState* S, HlmConst c, int p, const double* __restrict__ unif, HlmOut o,
+                                  const int* __restrict__ status) {
+  hlm_accept(*S, c, p, unif, o, *status != 0);
 }
 
 __device__ void hlm_init_state(HlmState& s) {
@@ -125,6 +135,7 @@ __device__ void hlm_init_state(HlmState& s) {
   s.quad = s.logdet = s.quad_p = s.logdet_p = 0.0;
   s.oob = 0;
   s.iter = 0;
+  s.fail_iter = 0;
 }
 
 __global__ void hlm_init_state_kernel(HlmState* S) { hlm_init_state(*S); }
@@ -338,10 +349,11 @@ hlm_small_kernel(int n, const double* __restrict__ cx, const double* __restrict_
       }
       s.logdet_p = al;
       s.quad_p = aq;
-      hlm_accept(s, c, p, unif, o);
+      hlm_accept(s, c, p, unif, o, bad != 0);
       if (step + 1 < total_steps) hlm_propose(s, c, step % 3, norm);      // the next proposal, in the same serial section
     }
     __syncthreads();
+    if (bad) break;                        // the reference stops in chol() here
   }
   if (tid == 0) {
     *Sg = s;
@@ -362,6 +374,30 @@ static int hlm_small_launch(int n, const double* cx, const double* cy, const dou
   SPW_CUDA(cudaFuncSetAttribute(hlm_small_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hlm_small_kernel<TYPE><<<1, HLM_SMALL_THREADS, smem, st>>>(n, cx, cy, y, S, c, norm, unif, ho, status);
   SPW_LAUNCHED();
+  return SPW_OK;
+}
+
+// status word and the iteration of the first failed chol() back to the host
+static int hlm_finish(HlmWorkspace& ws, HlmState* S, int* info_host, cudaStream_t st) {
+  int status = 0;
+  HlmState hs;
+  SPW_CUDA(cudaMemcpyAsync(&status, ws.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaMemcpyAsync(&hs, S, sizeof(HlmState), cudaMemcpyDeviceToHost, st));
+  SPW_CUDA(cudaStreamSynchronize(st));
+  if (info_host) {
+    info_host[0] = hs.fail_iter;          // 1-based iteration (0: the initial factorisation, or no failure)
+    info_host[1] = status;
+  }
+  if (status != 0) {
+    set_error("hlmBayes_sp: iteration %d: the leading minor of order %d is not positive (chol of sig2*R + tau2*I)",
+              hs.fail_iter, status);
+    return SPW_ERR_NOT_PD;
+  }
+  if (hs.fail_iter != 0) {                // no failed pivot, but a log-ratio that is not a number (NaN / Inf in y or coords):
+    set_error("hlmBayes_sp: iteration %d: the acceptance ratio is not a number (R: 'missing value where TRUE/FALSE "
+              "needed')", hs.fail_iter);  // the reference's `if(log(runif(1)) < accept.prob)` stops there
+    return SPW_ERR_NOT_PD;
+  }
   return SPW_OK;
 }
 
@@ -388,18 +424,7 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
         case 1: SPW_TRY(hlm_small_launch<1>(n, cx, cy, y_dev, S, c, norm_dev, unif_dev, ho, ws.status, st)); break;
         default: SPW_TRY(hlm_small_launch<2>(n, cx, cy, y_dev, S, c, norm_dev, unif_dev, ho, ws.status, st)); break;
       }
-      int status = 0;
-      SPW_CUDA(cudaMemcpyAsync(&status, ws.status, sizeof(int), cudaMemcpyDeviceToHost, st));
-      SPW_CUDA(cudaStreamSynchronize(st));
-      if (info_host) {
-        info_host[0] = 0;
-        info_host[1] = status;
-      }
-      if (status != 0) {
-        set_error("hlmBayes_sp: the leading minor of order %d is not positive (chol of sig2*R + tau2*I)", status);
-        return SPW_ERR_NOT_PD;
-      }
-      return SPW_OK;
+      return hlm_finish(ws, S, info_host, st);
     }
   }
   hlm_init_state_kernel<<<1, 1, 0, st>>>(S);
@@ -414,7 +439,7 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
     if (ws.dag) SPW_TRY(potrf_dag(*ws.dag, L, ws.dinv, ws.status, st));
     else SPW_TRY(potrf_batched(*ws.plan, L, ws.dinv, nullptr, 1, ws.status, st, ws.la));
     SPW_TRY(logdet_quad_batched(n, L, &S->logdet_p, &S->quad_p, 1, st));
-    hlm_accept_kernel<<<1, 1, 0, st>>>(S, c, p, unif_dev, ho);
+    hlm_accept_kernel<<<1, 1, 0, st>>>(S, c, p, unif_dev, ho, ws.status);
     SPW_LAUNCHED();
     return SPW_OK;
   };
@@ -450,18 +475,7 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
   } else {
     for (; done < niter; ++done) SPW_TRY(iteration());
   }
-  int status = 0;
-  SPW_CUDA(cudaMemcpyAsync(&status, ws.status, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SPW_CUDA(cudaStreamSynchronize(st));
-  if (info_host) {
-    info_host[0] = 0;
-    info_host[1] = status;
-  }
-  if (status != 0) {
-    set_error("hlmBayes_sp: the leading minor of order %d is not positive (chol of sig2*R + tau2*I)", status);
-    return SPW_ERR_NOT_PD;
-  }
-  return SPW_OK;
+  return hlm_finish(ws, S, info_host, st);
 }
 
 size_t hlm_state_bytes() { return sizeof(HlmState); }

@@ -351,8 +351,8 @@ def test_bayes_cwomb_riemann(spw, cov_type, phir):
     for k in ref:
         scale = max(np.abs(ref[k]).max(), 1.0)
         assert np.max(np.abs(np.asarray(got[k]) - ref[k])) < 1e-9 * scale, k
-    with pytest.raises(NotImplementedError):
-        spw.bayes_cwomb(coords=coords, model=model, cov_type=cov_type, nbatch=8, curve=curve, type="rectilinear")
+    with pytest.raises(ValueError):
+        spw.bayes_cwomb(coords=coords, model=model, cov_type=cov_type, nbatch=8, curve=curve, type="simpson")
 
 
 def test_hlm_summary(spw):
@@ -429,3 +429,45 @@ def test_gradient_kernel_variants_agree(spw, monkeypatch):
     old = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=2, eps=eps, return_moments=True, rounded=False)
     assert rel_err(tma["mean.grad"], old["mean.grad"], axis=2) < 1e-12
     assert rel_err(tma["var.grad"].reshape(4, -1, 25), old["var.grad"].reshape(4, -1, 25), axis=2) < 1e-12
+
+
+@pytest.mark.parametrize("S,G,nbatch", [(3000, 5, 3000), (4000, 37, 4), (100000, 3, 100000), (2600, 4, 1300), (70000, 2, 7)])
+def test_summary_scales_by_sorting(S, G, nbatch):
+    """hlm_summary / the wombling measure use one batch per sample (nb = S) and small nbatch means long batches: both
+    leave the rank-counting kernels for the bitonic-sort path (in shared memory up to 16384 values per row, global
+    passes above).  Bit-exact against the oracle's coda::HPDinterval restatement."""
+    import spwombling_b200 as spw
+    from oracle.summary import summarise_draws
+    rng = np.random.Generator(np.random.Philox(S + G))
+    draws = rng.standard_normal((S, G))
+    draws[::7] = np.round(draws[::7], 1)                     # ties
+    got = spw.hpd_summary(draws, nbatch)
+    assert np.array_equal(got, summarise_draws(draws, nbatch))
+
+
+def test_summary_propagates_nan():
+    """A NaN draw makes the affected estimates NaN (R: median / HPDinterval return NA) instead of silently 0."""
+    import spwombling_b200 as spw
+    rng = np.random.Generator(np.random.Philox(5))
+    for S, nbatch in ((60, 12), (3000, 3000)):
+        draws = rng.standard_normal((S, 4))
+        draws[S // 2, 1] = np.nan
+        got = spw.hpd_summary(draws, nbatch)
+        assert np.isnan(got[1]).all() and np.isfinite(got[[0, 2, 3]]).all()
+
+
+@pytest.mark.parametrize("n", [60, 300])
+def test_hlm_stops_at_a_non_finite_ratio(n):
+    """A proposal whose log-ratio is NaN must not be accepted through fmin(NaN, 0) = 0: the reference's
+    `if(log(runif(1)) < accept.prob)` raises an error at that iteration; here the chain rejects, records the iteration
+    and the call fails (both the single-CTA and the blocked chain)."""
+    import spwombling_b200 as spw
+    from spwombling_b200._lib import SpwError
+    rng = np.random.Generator(np.random.Philox(n))
+    coords = rng.random((n, 2))
+    y = rng.standard_normal(n)
+    y[3] = np.nan
+    with pytest.raises(SpwError) as e:
+        spw.hlmBayes_sp(y=y, coords=coords, niter=4, nburn=0, report=2, cov_type="matern2", norm=rng.standard_normal(12),
+                        unif=rng.random(12), verbose=False)
+    assert e.value.info[0] == 1                      # the first iteration
