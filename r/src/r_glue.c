@@ -3,8 +3,9 @@
  * Marshalling only: every wrapper checks types, allocates the R result vectors, calls one C-ABI entry point with
  * plain pointers, and turns a non-zero status into an R error (the reference stops in chol() there).
  *
- * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no R headers (Rinternals.h).  Build inside the
- * package with  PKG_LIBS = -L$(SPW_LIB_DIR) -lspwombling -lcudart  and  useDynLib(spWombling, .registration = TRUE).
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no R headers (Rinternals.h); tests/test_abi.py compiles it
+ * against stub headers with R CMD SHLIB's flags.  Build inside the package with src/Makevars (r/src/Makevars) and
+ * useDynLib(spWombling, .registration = TRUE) (r/patches/).
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -83,12 +84,43 @@ SEXP spw_r_surface_analysis(SEXP draws, SEXP S, SEXP g, SEXP nbatch) {
   return summ;
 }
 
+/* batch medians + median + coda::HPDinterval for the columns of an S x g matrix  --  R/spatial_gradient.R:391-419,
+ * R/hlm_summary.R:26-40 (nbatch = S: HPDinterval on the raw samples) */
+SEXP spw_r_hpd_summary(SEXP draws, SEXP nbatch, SEXP prob) {
+  const int S = Rf_nrows(draws), g = Rf_length(draws) / (S > 0 ? S : 1);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, g, 3));
+  spw_stop(spw_hpd_summary(S, g, Rf_asInteger(nbatch), Rf_asReal(prob), REAL(draws), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+/* bayes_cwomb(type = "rectilinear")  --  R/spatial_wombling.R:159-244, :308-393; eps is the 2 x nseg x S array of the
+ * rnorm() variates mvrnorm consumes; returns the 2 x (nseg x S) measures as an nseg x S x 2 array */
+SEXP spw_r_wombling_rect(SEXP type, SEXP coords, SEXP curve, SEXP rule_len, SEXP phi, SEXP sig2, SEXP z, SEXP eps) {
+  const int n = Rf_nrows(coords), nseg = Rf_nrows(curve) - 1, S = Rf_length(phi);
+  SEXP w = PROTECT(Rf_alloc3DArray(REALSXP, nseg, S, 2));
+  int info[4];
+  spw_stop(spw_wombling_rect_run(Rf_asInteger(type), n, REAL(coords), nseg, REAL(curve), Rf_asInteger(rule_len), S,
+                                 REAL(phi), REAL(sig2), REAL(z), REAL(eps), REAL(w), NULL, NULL, info));
+  UNPROTECT(1);
+  return w;
+}
+
+/* .onUnload */
+SEXP spw_r_shutdown(void) {
+  spw_shutdown();
+  return Rf_allocVector(INTSXP, 0);
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"spw_r_cov_delta", (DL_FUNC)&spw_r_cov_delta, 4},
   {"spw_r_hlm_run", (DL_FUNC)&spw_r_hlm_run, 10},
   {"spw_r_gradient_run", (DL_FUNC)&spw_r_gradient_run, 10},
   {"spw_r_spsample_run", (DL_FUNC)&spw_r_spsample_run, 7},
   {"spw_r_surface_analysis", (DL_FUNC)&spw_r_surface_analysis, 4},
+  {"spw_r_hpd_summary", (DL_FUNC)&spw_r_hpd_summary, 3},
+  {"spw_r_wombling_rect", (DL_FUNC)&spw_r_wombling_rect, 8},
+  {"spw_r_shutdown", (DL_FUNC)&spw_r_shutdown, 0},
   {NULL, NULL, 0}
 };
 

@@ -60,14 +60,44 @@ def test_argument_errors_without_gpu(lib_path):
         api.hlmBayes_sp(y=[1.0, 2.0], coords=[[0, 0], [1, 1]], niter=10, cov_type="matern1", verbose=False)
 
 
-def test_r_glue_compiles_against_stub():
-    """r/src/r_glue.c cannot be built here (no R), but it must at least be valid C whose calls match the prototypes
-    of include/spwombling.h: compile it with -fsyntax-only against a minimal stand-in for R's headers."""
+def test_r_glue_compiles_against_stub(lib_path, tmp_path):
+    """r/src/r_glue.c cannot be built with R here (no R), but it must be valid C whose calls match the prototypes of
+    include/spwombling.h: compile it the way `R CMD SHLIB` would (its default flags, -pedantic, -Werror) against a
+    minimal stand-in for R's headers, link it against libspwombling.so, and check that every spw_* symbol it needs is
+    exported by the library and every .Call routine it registers is defined."""
     import shutil
     import subprocess
     if not shutil.which("gcc"):
         pytest.skip("gcc not available")
-    cmd = ["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tools", "r_stub"),
-           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "r_glue.c")]
+    src = os.path.join(ROOT, "r", "src", "r_glue.c")
+    obj, so = str(tmp_path / "r_glue.o"), str(tmp_path / "spWombling.so")
+    cmd = ["gcc", "-std=gnu11", "-I", os.path.join(ROOT, "tools", "r_stub"), "-DNDEBUG", "-I", os.path.join(ROOT, "include"),
+           "-fpic", "-g", "-O2", "-Wall", "-pedantic", "-Werror", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    r = subprocess.run(["gcc", "-shared", "-o", so, obj, "-L", os.path.dirname(lib_path), "-lspwombling"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    und = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True).stdout
+    needed = sorted(set(re.findall(r"\b(spw_[a-z0-9_]+)\b", und)))
+    assert needed and set(needed) <= set(header_functions())
+    # everything else still undefined must be R's API (resolved by libR at load time) or libc
+    other = [ln.split()[-1] for ln in und.splitlines() if ln.strip() and "spw_" not in ln]
+    assert all(o.startswith(("Rf_", "R_", "REAL", "INTEGER", "SET_VECTOR_ELT", "XLENGTH", "_", "__")) or "@" in o for o in other), other
+    # the registration table matches the definitions and what the R side calls
+    csrc = open(src).read()
+    registered = re.findall(r'\{"(spw_r_[a-z_]+)", \(DL_FUNC\)&(spw_r_[a-z_]+), (\d+)\}', csrc)
+    assert registered and all(a == b for a, b, _ in registered)
+    rsrc = "".join(open(os.path.join(ROOT, "r", "R", f)).read() for f in sorted(os.listdir(os.path.join(ROOT, "r", "R"))))
+    for name, _, nargs in registered:
+        calls = re.findall(r"\.Call\(%s\b([^)]*)" % name, rsrc)
+        assert calls, "%s is registered but never .Call()ed from r/R" % name
+    for name in set(re.findall(r"\.Call\((spw_r_[a-z_]+)", rsrc)):
+        assert name in [a for a, _, _ in registered], "%s is .Call()ed but not registered" % name
+
+
+def test_r_packaging_files_exist():
+    for f in ("r/src/Makevars", "r/patches/NAMESPACE.patch", "r/patches/DESCRIPTION.patch", "r/R/zzz.R", "r/R/zz_gpu_backend.R"):
+        assert os.path.exists(os.path.join(ROOT, f)), f
+    assert "useDynLib(spWombling, .registration = TRUE)" in open(os.path.join(ROOT, "r/patches/NAMESPACE.patch")).read()
+    assert "spw_r_shutdown" in open(os.path.join(ROOT, "r/R/zzz.R")).read()
