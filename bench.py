@@ -366,26 +366,34 @@ def run_ours(args, w):
 
 
 def bench_hlm(spw, args):
-    """hlmBayes_sp iterations/s (BASELINE.json's second metric), N = 5000 matern2 and the README's N = 100."""
+    """hlmBayes_sp iterations/s (BASELINE.json's second metric), N = 5000 matern2 and the README's N = 100, through the
+    C ABI with host buffers (wall clock of spw_hlm_run: transfers, plan and graph set-up included)."""
+    peak_tf = 37.0
+    pk = os.path.join(ROOT, "profiles", "FP64_PEAK.json")
+    if os.path.exists(pk):
+        peak_tf = float(json.load(open(pk)).get("fp64_tensor_tflops", peak_tf))
     out = {}
-    for n, niter in ((5000, 24), (100, 2000)):
+    for n, niter in ((5000, 48), (100, 2000)):
         rng = np.random.Generator(np.random.Philox(2))
         coords = rng.random((n, 2))
         y = 10 * (np.sin(3 * np.pi * coords[:, 0]) + np.cos(3 * np.pi * coords[:, 1])) + rng.standard_normal(n)
         r6 = np.random.Generator(np.random.Philox(6))
         norm, unif = r6.standard_normal(3 * niter), r6.random(3 * niter)
         kw = dict(y=y, coords=coords, nburn=0, report=max(1, niter // 2), cov_type="matern2", verbose=False)
-        spw.hlmBayes_sp(niter=max(2, niter // 4), norm=norm, unif=unif, **kw)    # warm-up (plans, clocks)
+        spw.hlmBayes_sp(niter=max(2, niter // 8), norm=norm, unif=unif, **kw)    # warm-up (plans, clocks)
         dt = 1e30
         for _ in range(3):                                                       # best of 3 (wall clock, host jitter)
             t0 = time.perf_counter()
             spw.hlmBayes_sp(niter=niter, norm=norm, unif=unif, **kw)
             dt = min(dt, time.perf_counter() - t0)
         its = niter / dt
-        out["n%d" % n] = {"iters_per_s": its, "niter": niter,
-                          "cholesky_tflops": its * 3 * n ** 3 / 3.0 / 1e12,
-                          "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H included); 3 Cholesky "
-                                  "factorisations of order n+1 per iteration (n <= 200: single persistent CTA)"}
+        tf = its * 3 * (n + 1) ** 3 / 3.0 / 1e12
+        out["n%d" % n] = {"iters_per_s": its, "niter": niter, "ms_per_factorisation": dt / niter / 3 * 1e3,
+                          "cholesky_tflops": tf, "cholesky_frac": tf / peak_tf,
+                          "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H, plan and CUDA-graph set-up "
+                                  "included); 3 Cholesky factorisations of order n+1 per iteration ((n+1)^3/3 flop "
+                                  "each; n <= 200: single persistent CTA); cholesky_frac = cholesky_tflops / %.1f "
+                                  "(measured FP64 tensor peak)" % peak_tf}
     if not args.no_cpu:
         from oracle import baseline
         n = 5000

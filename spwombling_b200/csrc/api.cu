@@ -94,6 +94,13 @@ struct PhaseTimer {
   ~PhaseTimer() { collect(); }
 };
 
+// host wall-clock phases of spw_gradient_run (SPW_TIMING=1 prints them)
+static double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 // ---- per-device context -----------------------------------------------------------------------------
 struct DeviceCtx {
   cudaStream_t stream = nullptr;
@@ -360,8 +367,6 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
     SPW_CUDA(cudaStreamWaitEvent(ps, ctx->ev_start, 0));
   }
   PhaseTimer pt(st);
-  const char* env_main = getenv("SPW_MAIN");
-  const bool use_tma = !(env_main && env_main[0] == '0');
   int k = 0;
   for (int s0 = 0; s0 < S; s0 += B, ++k) {
     const int nb = std::min(B, S - s0), set = overlap ? (k & 1) : 0;
@@ -409,8 +414,7 @@ static int gradient_shard(int type, int n, const double* cx, const double* cy, i
       P.g_total = G;
       P.s_begin = s0;
       pt.begin(PH_MAIN, st);
-      if (use_tma) SPW_TRY(gradient_tma_launch(type, P, nb, st));
-      else SPW_TRY(gradient_main_launch(type, P, nb, st));
+      SPW_TRY(gradient_tma_launch(type, P, nb, st));
       pt.end();
       if (g_profile) {
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -476,16 +480,35 @@ static int spsample_shard(int type, int n, const double* cx, const double* cy, i
   for (int s0 = 0; s0 < S; s0 += B) {
     const int nb = std::min(B, S - s0);
     SPW_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 3 * B, st));
+    static const bool timing = getenv("SPW_TIMING") && getenv("SPW_TIMING")[0] == '1';
+    double tt[12];
+    int ti = 0;
+    auto tick = [&]() { if (timing) { cudaStreamSynchronize(st); tt[ti++] = wall_ms(); } };
+    tick();
     SPW_TRY(cov_assemble_batched(type, n, cx, cy, phi + s0, nullptr, jitter + s0, 1, L, nb, 1, st));
+    tick();
     SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status, st));
+    tick();
     SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    tick();
     SPW_TRY(gram_of_inverse_batched(*plan, Linv, L, nb, st));                       // R.inv.Z
+    tick();
     SPW_TRY(scale_add_diag_batched(n, L, inv_sig2 + s0, inv_tau2 + s0, nb, st));    // Sig.Z.in
+    tick();
     SPW_TRY(potrf_batched(*plan, L, dinv, &Linv, nb, status + B, st));
+    tick();
     SPW_TRY(trtri_batched(*plan, L, Linv, nb, st));
+    tick();
     SPW_TRY(gram_of_inverse_batched(*plan, Linv, L, nb, st));                       // Sig.Z
+    tick();
     SPW_TRY(gemv_batched(n, L, w + (long long)s0 * ldv, ldv, nullptr, 0, mu, ld, 0, nb, st));   // mu.Z
+    tick();
     SPW_TRY(potrf_batched(*plan, L, dinv, nullptr, nb, status + 2 * B, st));        // chol(Sig.Z)
+    tick();
+    if (timing)
+      fprintf(stderr, "[spw] spsample batch of %d (n = %d): cov %.2f potrf %.2f trtri %.2f gram %.2f scale %.2f potrf %.2f trtri "
+              "%.2f gram %.2f gemv %.2f potrf %.2f ms\n", nb, n, tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3],
+              tt[5] - tt[4], tt[6] - tt[5], tt[7] - tt[6], tt[8] - tt[7], tt[9] - tt[8], tt[10] - tt[9]);
     // z = t(chol(Sig.Z)) eps + mu.Z: the upper factor's transpose is this library's lower factor
     SPW_TRY(gemv_batched(n, L, eps + (long long)s0 * ldv, ldv, mu, ld, z_out + (long long)s0 * ldv, ldv, 1, nb, st));
     SPW_CUDA(cudaMemcpyAsync(hs.data(), status, sizeof(int) * 3 * B, cudaMemcpyDeviceToHost, st));
@@ -950,13 +973,6 @@ int spw_gradient_shard_dev(int type, int n, const double* coords_dev, int g, con
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   return gradient_shard(type, n, coords_dev, coords_dev + n, g, grid_dev, grid_dev + g, S, phi_dev, sig2_dev, z_dev,
                         ldz, eps_dev, out_draws_dev, out_mean_dev, out_var_dev, info, st);
-}
-
-// host wall-clock phases of spw_gradient_run (SPW_TIMING=1 prints them)
-static double wall_ms() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 // one device's share of spw_gradient_run: samples [s_lo, s_hi).  The shard's draws stay on the device

@@ -1,4 +1,4 @@
-// Fused TRMM + Gram + draw kernel of the spatial_gradient path (see gradient.cu).
+// Fused TRMM + Gram + draw kernel of the spatial_gradient path (see gradient_tma.cu).
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
@@ -24,9 +24,7 @@ struct GradParams {
   int s_begin;
 };
 
-// cp.async / __syncthreads version (gradient.cu; kept as a cross-check, SPW_MAIN=0)
-int gradient_main_launch(int type, const GradParams& P, int batch, cudaStream_t st);
-// TMA + mbarrier + warp-specialised version (gradient_tma.cu; default)
+// TMA + mbarrier + warp-specialised kernel (gradient_tma.cu)
 int gradient_tma_launch(int type, const GradParams& P, int batch, cudaStream_t st);
 
 }  // namespace spw

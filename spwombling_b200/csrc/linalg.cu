@@ -22,7 +22,6 @@ namespace spw {
 // (zero-filled by TMA), so the only masking left is the triangular one.
 //   L: 128 x 128, 3 stages, 1 CTA/SM   (long-k products of the triangular inverse)
 //   M: 128 x  64, 2 stages, 2 CTA/SM   (Cholesky panel / trailing updates: the second CTA hides the C read-modify-write)
-//   S:  64 x  64, 3 stages, 2 CTA/SM   (kept for experiments)
 //   T:  32 x  64, 2 stages, 3 CTA/SM   (every step of a single matrix: many short CTAs; for the panel product rows,
 //                                       not columns, are split because it overwrites its own A operand)
 // ---------------------------------------------------------------------------------------------------
@@ -39,7 +38,6 @@ struct GCfg {
 };
 using GCfgL = GCfg<128, 128, 3, 1>;
 using GCfgM = GCfg<128, 64, 2, 2>;
-using GCfgS = GCfg<64, 64, 3, 2>;
 using GCfgT = GCfg<32, 64, 2, 3>;
 }  // namespace
 
@@ -261,7 +259,7 @@ static GemmTask blank_task() {
 }
 
 static void shape_dims(int shape, int& tm, int& tn) {
-  tm = (shape == 3) ? 32 : (shape == 2) ? 64 : 128;
+  tm = (shape == 3) ? 32 : 128;
   tn = (shape == 0) ? 128 : 64;
 }
 
@@ -470,14 +468,14 @@ static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand 
   return SPW_OK;
 }
 
-// shape: 0 = L (128 x 128), 1 = M (128 x 64), 2 = S (64 x 64), 3 = T (32 x 64); the task list must have been tiled accordingly
+// shape: 0 = L (128 x 128), 1 = M (128 x 64), 3 = T (32 x 64); the task list must have been tiled accordingly
 static int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
                              MatView CT, double alpha, cudaStream_t st, bool one_per_sm = false) {
   switch (shape) {
     case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
     case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
     case 3: return launch_gemm_cfg<GCfgT>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
-    default: return launch_gemm_cfg<GCfgS>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
+    default: set_error("gemm: unknown tile shape %d", shape); return SPW_ERR_ARG;
   }
 }
 

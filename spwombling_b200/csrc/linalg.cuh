@@ -17,7 +17,7 @@ struct GemmTask {
   int c_row, c_col;     // origin of the C tile
   int ct_row, ct_col;   // origin of the transposed store (row = n index, col = m index)
   int m, n, k;          // extents
-  int a_tri, a_lim0, b_tri, b_lim0;   // see gemm_nt.cuh TriMask
+  int a_tri, a_lim0, b_tri, b_lim0;   // 0: none, 1: zero for k > lim0 + row, 2: zero for k < lim0 + row (triangular operands)
   int flags;            // GT_*
 };
 enum : int { GT_ACCUM = 1, GT_STORE = 2, GT_STORE_T = 4 };
@@ -34,7 +34,7 @@ struct LinalgPlan {
   int n = 0;            // matrix order the plan was built for
   int rows = 0;         // rows actually factored (n, or n + 1 for the augmented hlm system)
   int nblk = 0;
-  int shape_panel = 1, shape_inner = 1, shape_outer = 1;   // GEMM tile shapes (0: 128x128, 1: 128x64, 2: 64x64, 3: 32x64)
+  int shape_panel = 1, shape_inner = 1, shape_outer = 1;   // GEMM tile shapes (0: 128x128, 1: 128x64, 3: 32x64)
   std::vector<ChunkRange> panel, trail;         // per 64-wide potrf step (trail: inside the outer block)
   std::vector<ChunkRange> outer;                // per outer block: update of everything to its right
   std::vector<ChunkRange> outer_next, outer_bulk;   // the same tasks split: next outer block's columns / the rest

@@ -115,11 +115,11 @@ __device__ __forceinline__ int dag_rstart(int b, int n, int rows, int nblk) {
 // blocks of a row that the chain CTA takes over, when it loads them.  A late bulk update therefore never holds up the
 // single-column updates of the same block; its only deadline is that merge.
 __device__ __forceinline__ int dag_s0(int c) { return OUTER * max(0, c / OUTER - 1); }
-// does this single-column update merge the bulk buffer?  The last one a sub-worker applies to the block: source c - 1,
-// or source R - 3 for the three blocks (R, R-2 .. R) of a row that the chain CTA finishes itself (it applies the
-// sources R - 2, R - 1 in shared memory and never reads the bulk buffer).
+// does this single-column update merge the bulk buffer?  The last source (c - 1) of a block below the band of the chain
+// CTA; the three blocks (R, R-2 .. R) of a row that the chain finishes itself are merged by the chain when it loads
+// them at step R - 1 (the bulk updates onto them then have three more steps than the last helper update would leave).
 __device__ __forceinline__ bool dag_merges(const DagTask& t) {
-  return t.type == 1 && t.k1 - t.k0 == 1 && t.nrb == 1 && dag_s0(t.cb) > 0 && t.k0 == min(t.cb - 1, t.rb - 3);
+  return t.type == 1 && t.k1 - t.k0 == 1 && t.k0 == t.cb - 1 && t.rb >= t.cb + 3 && dag_s0(t.cb) > 0;
 }
 
 // One polling round over the flags a task depends on (warp-collective; every lane reads at most one flag).
@@ -440,8 +440,8 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
       auto bg_sync = [&]() { asm volatile("bar.sync 5, 128;\n" ::: "memory"); };
       if (has_r1) {
         if (bw == 0) {
-          // the helpers have applied every source k < j - 1 to the three blocks (the last single-column update of each
-          // has merged the bulk buffer of the block)
+          // the helpers have applied every source k < j - 1 to the three blocks: the single-column updates in place
+          // (main flag) and the bulk updates in the bulk buffer (fb), which is merged while loading
           const int want = max(0, j - 1);
           bool ok;
           do {
@@ -449,23 +449,26 @@ __device__ __forceinline__ void dag_chain_band(const DagParams& P, unsigned char
             if (lane == 0 && j >= 1) ok = (ld_acquire(P.upd + i1 * P.nblk + (j - 1)) == want);
             if (lane == 1) ok = (ld_acquire(P.upd + i1 * P.nblk + j) == want);
             if (lane == 2 && r1_col) ok = (ld_acquire(P.upd + i1 * P.nblk + i1) == want);
+            if (lane == 3 && j >= 1) ok = (ld_acquire(P.fb + i1 * P.nblk + (j - 1)) == dag_s0(j - 1));
+            if (lane == 4) ok = (ld_acquire(P.fb + i1 * P.nblk + j) == dag_s0(j));
+            if (lane == 5 && r1_col) ok = (ld_acquire(P.fb + i1 * P.nblk + i1) == dag_s0(i1));
           } while (!__all_sync(0xffffffffu, ok));
         }
         bg_sync();
         if (P.trace && bt == 0) s_ct[1] = (unsigned)(globaltimer() - t0);
         if (j >= 1) {
           const long long o = (long long)r1 * ld + (j - 1) * NB;
-          chain_load_tile<128>(sm.bufT, Lg + o, nullptr, ld, nr, NB, bt);
+          chain_load_tile<128>(sm.bufT, Lg + o, dag_s0(j - 1) > 0 ? P.Bp + o : nullptr, ld, nr, NB, bt);
         }
         {
           const long long o = (long long)r1 * ld + j * NB;
-          chain_load_tile<128>(Xcur, Lg + o, nullptr, ld, nr, cs(j), bt);
+          chain_load_tile<128>(Xcur, Lg + o, dag_s0(j) > 0 ? P.Bp + o : nullptr, ld, nr, cs(j), bt);
         }
       }
       asm volatile("bar.sync 4, 512;\n" ::: "memory");      // the sweep threads hold block j in registers: bufS is free
       if (has_r1 && r1_col) {
         const long long o = (long long)r1 * ld + i1 * NB;
-        chain_load_tile<128>(sm.bufS, Lg + o, nullptr, ld, nr, cs(i1), bt);
+        chain_load_tile<128>(sm.bufS, Lg + o, dag_s0(i1) > 0 ? P.Bp + o : nullptr, ld, nr, cs(i1), bt);
       }
       bg_sync();
       if (has_r1 && j >= 1) {
@@ -746,7 +749,14 @@ int dag_plan_build(DagPlan& plan, int n, int extra_rows) {
           DagTask t;
           memset(&t, 0, sizeof(t));
           t.type = 1; t.cb = (short)c; t.k0 = (short)kk.first; t.k1 = (short)kk.second;
-          for (int b = c; b < nrb; b += 2) {
+          // the three blocks next to the diagonal are what the chain CTA waits for: one-block tiles (half the time of a
+          // two-block tile), first in the column
+          int b = c;
+          for (; b < std::min(nrb, c + 3); ++b) {
+            t.rb = (short)b; t.nrb = 1;
+            bulk.push_back(t);
+          }
+          for (; b < nrb; b += 2) {
             t.rb = (short)b; t.nrb = (short)std::min(2, nrb - b);
             bulk.push_back(t);
           }

@@ -420,17 +420,6 @@ def test_gradient_edge_shapes(spw, n, G, cov_type, phir):
     assert rel_err(got_d, want_d, axis=2) < RTOL
 
 
-def test_gradient_kernel_variants_agree(spw, monkeypatch):
-    """The cp.async / __syncthreads kernel (SPW_MAIN=0) and the default TMA kernel compute the same quantities."""
-    coords, grid, phi, sig2, z, eps = synth(300, 5, 4, "matern2", (15, 40), seed=3)
-    model = {"phi": phi, "sig2": sig2, "z": z}
-    tma = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=2, eps=eps, return_moments=True, rounded=False)
-    monkeypatch.setenv("SPW_MAIN", "0")
-    old = spw.spatial_gradient(coords, model, "matern2", grid, nbatch=2, eps=eps, return_moments=True, rounded=False)
-    assert rel_err(tma["mean.grad"], old["mean.grad"], axis=2) < 1e-12
-    assert rel_err(tma["var.grad"].reshape(4, -1, 25), old["var.grad"].reshape(4, -1, 25), axis=2) < 1e-12
-
-
 @pytest.mark.parametrize("S,G,nbatch", [(3000, 5, 3000), (4000, 37, 4), (100000, 3, 100000), (2600, 4, 1300), (70000, 2, 7)])
 def test_summary_scales_by_sorting(S, G, nbatch):
     """hlm_summary / the wombling measure use one batch per sample (nb = S) and small nbatch means long batches: both
