@@ -298,6 +298,27 @@ def run_ours(args, w):
     h2d = (S_total * (2 + n + G * c) + coords.size + grid.size) * 8
     d2h = (c * 3 * G + S_total * c * G) * 8
     out_e2e = step_e2e(last_i)
+    # ---- optional: the WHOLE job of the workload (all S posterior samples, nbatch = 200) through spw_gradient_run, wall
+    #      clock including input marshalling, every H2D / D2H copy, the gather and the summary ----
+    full_job = None
+    if args.full_job:
+        if rank == 0:
+            Sf = args.full_job
+            fin = make_inputs(w, Sf, seed0=7000)
+            t0 = time.perf_counter()
+            fo = spw.spatial_gradient(fin[0], {"phi": fin[2], "sig2": fin[3], "z": fin[4]}, cov, fin[1], nbatch=200,
+                                      return_mcmc=True, eps=fin[5], ngpu=world, rounded=False)
+            dt = time.perf_counter() - t0
+            from oracle.summary import summarise_draws
+            sub = np.linspace(0, G - 1, 7).astype(int)
+            ok = all(np.array_equal(summarise_draws(np.asarray(fo["grad.%s.mcmc" % nm])[:, sub], 200), fo[en][sub])
+                     for nm, en in zip(("s1", "s2", "s11", "s12", "s22")[:c],
+                                       ("grad1.est", "grad2.est", "grad11.est", "grad12.est", "grad22.est")[:c]))
+            full_job = {"samples": Sf, "grid_points": G, "nbatch": 200, "ngpu": world, "wall_s": dt,
+                        "units_per_s_wall": Sf * G / dt, "h2d_gb": (fin[5].nbytes + fin[4].nbytes) / 1e9,
+                        "d2h_gb": Sf * G * c * 8 / 1e9, "summary_matches_oracle_on_returned_draws": bool(ok)}
+            del fin, fo
+        barrier_host()
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -324,7 +345,9 @@ def run_ours(args, w):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "main_kernel_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+        rec = json.load(open(tp)).get(args.workload)
+        if rec:     # ncu capture of one launch, scaled to the average number of samples per launch of this run
+            traffic = rec["bytes_per_sample"] * (hi - lo) * args.steps / main_calls
     names_ph = ["cov_assemble", "potrf", "trtri", "trmv", "cross_cov", "gradient_main"]
     phases = {nm: {"ms_per_step": ph_ms[i] / args.steps, "launch_groups": int(ph_calls[i])} for i, nm in enumerate(names_ph)}
     roofline = {"bound": "tensor", "kernel": "gradient_tma_kernel (TMA-fed fused TRMM + Gram + 5x5 chol + draw)",
@@ -334,7 +357,8 @@ def run_ours(args, w):
                                "MEASURED_PEAKS.json has no FP64 entry)",
                 "ms_per_launch": main_ms / main_calls, "flops_per_launch": main_flops.value / main_calls,
                 "share_of_step": main_ms / ms_total,
-                "note": "rank 0's launches; traffic is per launch of 8 samples (ncu --set full, profiles/)"}
+                "note": "rank 0's launches; traffic = DRAM bytes per launch from one ncu --set full capture "
+                        "(profiles/main_kernel_traffic.json), scaled to this run's samples per launch"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -350,6 +374,8 @@ def run_ours(args, w):
             "parity": {"gathered_sample_vs_single_rank_recompute": "bit-identical",
                        "c_abi_path_vs_torch_distributed_path": "bit-identical (draws of the last sample and all estimates)"},
             "gpu_launches": int(launches), "roofline": roofline, "phases": phases}
+    if full_job:
+        line["full_job"] = full_job
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     if world == 1 and not args.no_cpu:
         r = cpu_baseline_leg(w)
@@ -444,6 +470,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="posterior samples per step (whole job, split over the ranks)")
+    ap.add_argument("--full-job", type=int, default=0, metavar="S",
+                    help="also run the workload's whole job with S posterior samples through spw_gradient_run (wall clock)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-hlm", action="store_true", help="skip the hlmBayes_sp secondary metric")
     args = ap.parse_args()
