@@ -383,7 +383,10 @@ def run_ours(args, w):
                                 "sample": r["sample"], "host": r["host"]}
     # ---- secondary metric: hlmBayes_sp MCMC iterations / s at 1 GPU ----
     if world == 1 and not args.no_hlm:
-        line["hlm"] = bench_hlm(spw, args)
+        try:                                  # a secondary metric must never take the headline line down with it
+            line["hlm"] = bench_hlm(spw, args)
+        except Exception as exc:              # noqa: BLE001 -- reported, not swallowed
+            line["hlm"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         line["spsample"] = bench_spsample(spw, args)
     if world > 1:
         dist.barrier()
@@ -416,9 +419,12 @@ def bench_hlm(spw, args):
         tf = its * 3 * (n + 1) ** 3 / 3.0 / 1e12
         out["n%d" % n] = {"iters_per_s": its, "niter": niter, "ms_per_factorisation": dt / niter / 3 * 1e3,
                           "cholesky_tflops": tf, "cholesky_frac": tf / peak_tf,
+                          "schedule": ("single persistent CTA" if n <= 200 else
+                                       "shadow schedule (SPW_LA=0)" if os.environ.get("SPW_LA", "")[:1] == "0" or n < 2048
+                                       else "look-ahead schedule with a resident diagonal chain (potrf_la.cu)"),
                           "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H, plan and CUDA-graph set-up "
                                   "included); 3 Cholesky factorisations of order n+1 per iteration ((n+1)^3/3 flop "
-                                  "each; n <= 200: single persistent CTA); cholesky_frac = cholesky_tflops / %.1f "
+                                  "each); cholesky_frac = cholesky_tflops / %.1f "
                                   "(measured FP64 tensor peak)" % peak_tf}
     if not args.no_cpu:
         from oracle import baseline

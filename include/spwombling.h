@@ -67,6 +67,9 @@ int spw_debug_diag_timing(long long* out16);
  * appended rows) on the current device; 4 words per task (packed id, start ns, end ns, 2 * SM + sub-worker).
  * Returns the number of words written (<= cap_words). */
 long long spw_debug_dag_trace(int n, int extra, unsigned long long* out, long long cap_words);
+/* diagnostic: mean CUDA-event time (ms) of one single-matrix factorisation of order n under the schedule the environment selects */
+int spw_debug_potrf_time(int n, int extra, int reps, double* ms_out, int* info);
+long long spw_debug_la_trace(int n, int extra, unsigned long long* out, long long cap_words);
 
 /* covariance kernels ----------------------------------------------------------------------------
  * spw_cov: as.matrix(dist(coords)) fused with cov_gaussian / cov_matern1 / cov_matern2

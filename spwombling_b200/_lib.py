@@ -32,6 +32,8 @@ SIGNATURES = {
     "spw_profile_read": (c_int, [c_vp, c_vp, c_vp, c_int]),
     "spw_debug_diag_timing": (c_int, [c_vp]),
     "spw_debug_dag_trace": (c_ll, [c_int, c_int, c_vp, c_ll]),
+    "spw_debug_potrf_time": (c_int, [c_int, c_int, c_int, c_vp, c_vp]),
+    "spw_debug_la_trace": (c_ll, [c_int, c_int, c_vp, c_ll]),
     "spw_cov": (c_int, [c_int, c_int, c_vp, c_dbl, c_dbl, c_vp]),
     "spw_cov_delta": (c_int, [c_int, c_ll, c_vp, c_dbl, c_dbl, c_vp]),
     "spw_cross_cov": (c_int, [c_int, c_int, c_vp, c_int, c_vp, c_dbl, c_vp]),

@@ -10,7 +10,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libspwombling.so")
-SOURCES = ["api.cu", "cov.cu", "linalg.cu", "potrf_dag.cu", "wombling.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
+SOURCES = ["api.cu", "cov.cu", "linalg.cu", "potrf_dag.cu", "potrf_la.cu", "wombling.cu", "gradient_tma.cu", "tma.cu", "summary.cu", "hlm.cu"]
 # cov.cu is compiled without FMA contraction: its elementwise formulas then round exactly like the reference's
 # R arithmetic (and K[i][j] == K[j][i] bit for bit, whichever thread computes it)
 # wombling.cu likewise: its double quadrature relies on t2 - t1 being exactly zero on the diagonal node pairs (the

@@ -20,6 +20,7 @@
 #include "hlm.cuh"
 #include "linalg.cuh"
 #include "potrf_dag.cuh"
+#include "potrf_la.cuh"
 #include "summary.cuh"
 #include "tma.cuh"
 #include "wombling.cuh"
@@ -106,6 +107,8 @@ struct DeviceCtx {
   cudaStream_t stream = nullptr;
   std::map<std::tuple<int, int, int>, LinalgPlan*> plans;
   std::map<std::pair<int, int>, DagPlan*> dag_plans;
+  std::map<std::pair<int, int>, LaPlan*> la_plans;
+  LaStreams la_streams;        // side / bulk streams and events of the look-ahead Cholesky (potrf_la.cu)
   void* ws = nullptr;          // grow-only workspace
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
@@ -202,6 +205,34 @@ static int get_dag_plan(DeviceCtx& c, int n, int extra, const DagPlan** out) {
     it = c.dag_plans.emplace(key, p).first;
   }
   *out = it->second;
+  return SPW_OK;
+}
+
+// Look-ahead schedule for one matrix of order n (nullptr: use potrf_batched): the default from order 2048 on, where
+// it is 4-7 % faster than the shadow schedule.  SPW_LA=0 disables it, SPW_LA_MIN sets the smallest order it is used for.
+static int get_la_plan(DeviceCtx& c, int n, int extra, const LaPlan** out, LaStreams** streams) {
+  *out = nullptr;
+  *streams = nullptr;
+  const char* env = getenv("SPW_LA");
+  if (env && env[0] == '0') return SPW_OK;
+  const char* env_min = getenv("SPW_LA_MIN");
+  const int nmin = env_min ? atoi(env_min) : 2048;
+  if (n < nmin) return SPW_OK;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto key = std::make_pair(n, extra);
+  auto it = c.la_plans.find(key);
+  if (it == c.la_plans.end()) {
+    LaPlan* p = new LaPlan();
+    int rc = la_plan_build(*p, n, extra);
+    if (rc != SPW_OK) {
+      delete p;
+      return rc;
+    }
+    it = c.la_plans.emplace(key, p).first;
+  }
+  SPW_TRY(la_streams_reserve(c.la_streams, it->second->nblk));
+  *out = it->second;
+  *streams = &c.la_streams;
   return SPW_OK;
 }
 
@@ -723,6 +754,98 @@ long long spw_debug_dag_trace(int n, int extra, unsigned long long* out, long lo
   return cnt;
 }
 
+// diagnostic: average time (ms, CUDA events) of one single-matrix factorisation of order n (+ extra appended rows) under the
+// schedule the environment selects (SPW_DAG / SPW_LA / SPW_LOOKAHEAD), replayed `reps` times as a CUDA graph on a
+// synthetic positive definite matrix.  info[0] = status of the last factorisation.
+__global__ void debug_fill_kernel(double* __restrict__ a, long long ld, int rows, int n) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows || j >= n) return;
+  const int d = i > j ? i - j : j - i;
+  a[(long long)i * ld + j] = (i < n ? exp(-0.02 * d) + (d == 0 ? 1.0 : 0.0) : 1.0);
+}
+
+// diagnostic (SPW_LA_TRACE=1): per diagonal step of the last look-ahead factorisation of order n: wait begins, step
+// begins, step published (globaltimer ns).  Returns the words written.
+long long spw_debug_la_trace(int n, int extra, unsigned long long* out, long long cap_words) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  DeviceCtx& c = g_ctx[dev & 63];
+  auto it = c.la_plans.find(std::make_pair(n, extra));
+  if (it == c.la_plans.end()) return 0;
+  cudaDeviceSynchronize();
+  std::vector<unsigned long long> v;
+  if (la_trace_read(*it->second, v) != SPW_OK) return -1;
+  const long long cnt = std::min<long long>((long long)v.size(), cap_words);
+  if (out && cnt > 0) memcpy(out, v.data(), sizeof(unsigned long long) * cnt);
+  return cnt;
+}
+
+int spw_debug_potrf_time(int n, int extra, int reps, double* ms_out, int* info) {
+  DeviceCtx* ctx;
+  SPW_TRY(get_ctx(&ctx));
+  cudaStream_t st = ctx->stream;
+  const LinalgPlan* plan;
+  SPW_TRY(get_plan(*ctx, n, extra, 1, &plan));
+  const long long ld = pad_ld(n);
+  const int rows = n + extra;
+  DevBuf dm, d0, dd, ds;
+  SPW_TRY(dm.alloc(sizeof(double) * rows * ld));
+  SPW_TRY(d0.alloc(sizeof(double) * rows * ld));
+  SPW_TRY(dd.alloc(sizeof(double) * plan->nblk * NB * NB));
+  SPW_TRY(ds.alloc(sizeof(int)));
+  debug_fill_kernel<<<dim3(ceil_div(n, 256), rows), 256, 0, st>>>(d0.as<double>(), ld, rows, n);
+  SPW_LAUNCHED();
+  MatView L{dm.as<double>(), ld, (long long)rows * ld};
+  const DagPlan* dag;
+  SPW_TRY(get_dag_plan(*ctx, n, extra, &dag));
+  const LaPlan* lap;
+  LaStreams* las;
+  SPW_TRY(get_la_plan(*ctx, n, extra, &lap, &las));
+  Lookahead* la;
+  SPW_TRY(get_lookahead(*ctx, n, &la));
+  const bool eager = reps < 0;             // reps < 0: plain stream launches instead of a CUDA graph
+  if (eager) reps = -reps;
+  auto factor = [&]() -> int {
+    if (dag) return potrf_dag(*dag, L, dd.as<double>(), ds.as<int>(), st);
+    if (lap) return potrf_lookahead(*lap, *las, L, dd.as<double>(), ds.as<int>(), st);
+    return potrf_batched(*plan, L, dd.as<double>(), nullptr, 1, ds.as<int>(), st, la);
+  };
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (!eager) {
+    SPW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = factor();
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != SPW_OK) return rc;
+    SPW_CUDA(ce);
+    SPW_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  }
+  std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+  for (auto& e : ev) SPW_CUDA(cudaEventCreate(&e));
+  for (int r = -2; r < reps; ++r) {
+    SPW_CUDA(cudaMemcpyAsync(dm.p, d0.p, sizeof(double) * rows * ld, cudaMemcpyDeviceToDevice, st));
+    SPW_CUDA(cudaMemsetAsync(ds.p, 0, sizeof(int), st));
+    if (r >= 0) SPW_CUDA(cudaEventRecord(ev[2 * r], st));
+    if (eager) SPW_TRY(factor());
+    else SPW_CUDA(cudaGraphLaunch(exec, st));
+    if (r >= 0) SPW_CUDA(cudaEventRecord(ev[2 * r + 1], st));
+    if (eager) SPW_CUDA(cudaStreamSynchronize(st));
+  }
+  SPW_CUDA(cudaStreamSynchronize(st));
+  double total = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    float ms = 0.f;
+    SPW_CUDA(cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]));
+    total += ms;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  if (ms_out) *ms_out = total / std::max(1, reps);
+  if (info) SPW_CUDA(cudaMemcpy(info, ds.p, sizeof(int), cudaMemcpyDeviceToHost));
+  return SPW_OK;
+}
+
 int spw_shutdown(void) {
   int cur = 0, ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess) return SPW_OK;
@@ -741,6 +864,21 @@ int spw_shutdown(void) {
       delete kv.second;
     }
     c.dag_plans.clear();
+    for (auto& kv : c.la_plans) {
+      la_plan_free(*kv.second);
+      delete kv.second;
+    }
+    c.la_plans.clear();
+    if (c.la_streams.side) cudaStreamDestroy(c.la_streams.side);
+    for (int i = 0; i < LaStreams::NBULK; ++i) {
+      if (c.la_streams.bulk[i]) cudaStreamDestroy(c.la_streams.bulk[i]);
+      if (c.la_streams.ev_bjoin[i]) cudaEventDestroy(c.la_streams.ev_bjoin[i]);
+    }
+    for (auto* v : {&c.la_streams.ev_p, &c.la_streams.ev_g})
+      for (auto e : *v) cudaEventDestroy(e);
+    if (c.la_streams.ev_fork) cudaEventDestroy(c.la_streams.ev_fork);
+    if (c.la_streams.ev_join) cudaEventDestroy(c.la_streams.ev_join);
+    c.la_streams = LaStreams();
     if (c.ws) cudaFree(c.ws);
     c.ws = nullptr;
     c.ws_bytes = 0;
@@ -871,8 +1009,13 @@ int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) 
   MatView L{dm.as<double>(), ld, (long long)n * ld};
   const DagPlan* dag;
   SPW_TRY(get_dag_plan(*ctx, n, 0, &dag));
+  const LaPlan* lap;
+  LaStreams* las;
+  SPW_TRY(get_la_plan(*ctx, n, 0, &lap, &las));
   if (dag) {
     SPW_TRY(potrf_dag(*dag, L, dd.as<double>(), ds.as<int>(), st));
+  } else if (lap) {
+    SPW_TRY(potrf_lookahead(*lap, *las, L, dd.as<double>(), ds.as<int>(), st));
   } else {
     Lookahead* la;
     SPW_TRY(get_lookahead(*ctx, n, &la));
@@ -888,6 +1031,11 @@ int spw_chol(int n, const double* a, double* u, double* logdet_half, int* info) 
   SPW_CUDA(cudaMemcpyAsync(&ld_half, dl.p, sizeof(double), cudaMemcpyDeviceToHost, st));
   SPW_CUDA(cudaStreamSynchronize(st));
   if (info) *info = status;
+  if (status == LA_STALLED) {
+    set_error("chol: the kernels of the look-ahead schedule did not run at the same time (a profiler that replays kernels "
+              "one by one, or a time-sliced GPU); set SPW_LA=0");
+    return SPW_ERR_CUDA;
+  }
   if (status) {
     set_error("the leading minor of order %d is not positive", status);
     return SPW_ERR_NOT_PD;
@@ -948,6 +1096,7 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   ws.plan = plan;
   SPW_TRY(get_lookahead(*ctx, n, &ws.la));
   SPW_TRY(get_dag_plan(*ctx, n, 1, &ws.dag));
+  SPW_TRY(get_la_plan(*ctx, n, 1, &ws.lap, &ws.las));
   int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
                        b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
                        o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);

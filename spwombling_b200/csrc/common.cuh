@@ -47,6 +47,28 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// ---- flags in global memory between CTAs / kernels that run at the same time -----------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes of other SMs are read here through the async proxy (TMA) and vice versa
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+
 // ---- cp.async (LDGSTS), 16-byte, L2-only (.cg) with zero-fill of the bytes past src_bytes -------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));

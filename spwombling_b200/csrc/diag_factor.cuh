@@ -113,7 +113,9 @@ __device__ __forceinline__ void diag_sync() {
 // BAND (persistent tile-DAG kernel, chain CTA): only the DIAG_THREADS sweep threads call this; the block is read from
 // the shared-memory buffer `src` (row-major, leading dimension DIAG_SRC_LD) and, once every thread has its part in
 // registers, the sweep threads arrive on named barrier 4 (CTA-wide count) so that the other warps may reuse `src`.
-template <bool CG, bool BAND = false>
+// SMEM_SRC without BAND (look-ahead diagonal kernel): the whole CTA calls this, the block is read from `src`, plain
+// CTA barriers.
+template <bool CG, bool BAND = false, bool SMEM_SRC = BAND>
 __device__ __forceinline__ void diag_factor_block(DiagSmem& sm, MatView L, int b, int blk, int n,
                                                   double* __restrict__ dinv, int nblk, MatView linv, int has_linv,
                                                   int* __restrict__ status, long long* __restrict__ dbg,
@@ -162,7 +164,7 @@ __device__ __forceinline__ void diag_factor_block(DiagSmem& sm, MatView L, int b
         const int row = 4 * ti + r, col = 4 * tk + q;
         double v = (row == col) ? 1.0 : 0.0;
         if (row < bs && col <= row) {
-          if constexpr (BAND) v = src[row * DIAG_SRC_LD + col];
+          if constexpr (SMEM_SRC) v = src[row * DIAG_SRC_LD + col];
           else v = CG ? __ldcg(Lp + (long long)row * L.ld + col) : Lp[(long long)row * L.ld + col];
         }
         a[r][q] = v;

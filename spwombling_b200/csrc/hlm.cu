@@ -388,6 +388,11 @@ static int hlm_finish(HlmWorkspace& ws, HlmState* S, int* info_host, cudaStream_
     info_host[0] = hs.fail_iter;          // 1-based iteration (0: the initial factorisation, or no failure)
     info_host[1] = status;
   }
+  if (status == LA_STALLED) {
+    set_error("hlmBayes_sp: iteration %d: the kernels of the look-ahead Cholesky did not run at the same time (a profiler "
+              "that replays kernels one by one, or a time-sliced GPU); set SPW_LA=0", hs.fail_iter);
+    return SPW_ERR_CUDA;
+  }
   if (status != 0) {
     set_error("hlmBayes_sp: iteration %d: the leading minor of order %d is not positive (chol of sig2*R + tau2*I)",
               hs.fail_iter, status);
@@ -437,6 +442,7 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
     SPW_TRY(cov_assemble_batched(type, n, cx, cy, &S->prop[2], &S->prop[0], &S->prop[1], 0, L, 1, 1, st));
     SPW_CUDA(cudaMemcpyAsync(ws.L + (long long)n * ws.ld, y_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     if (ws.dag) SPW_TRY(potrf_dag(*ws.dag, L, ws.dinv, ws.status, st));
+    else if (ws.lap) SPW_TRY(potrf_lookahead(*ws.lap, *ws.las, L, ws.dinv, ws.status, st));
     else SPW_TRY(potrf_batched(*ws.plan, L, ws.dinv, nullptr, 1, ws.status, st, ws.la));
     SPW_TRY(logdet_quad_batched(n, L, &S->logdet_p, &S->quad_p, 1, st));
     hlm_accept_kernel<<<1, 1, 0, st>>>(S, c, p, unif_dev, ho, ws.status);

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "linalg.cuh"
 #include "potrf_dag.cuh"
+#include "potrf_la.cuh"
 
 namespace spw {
 
@@ -16,6 +17,8 @@ struct HlmWorkspace {
   HlmState* state = nullptr;
   const LinalgPlan* plan = nullptr;   // built with extra_rows = 1
   Lookahead* la = nullptr;            // optional lookahead schedule of the Cholesky
+  const LaPlan* lap = nullptr;        // look-ahead schedule (potrf_la.cu); overrides plan / la
+  LaStreams* las = nullptr;
   const DagPlan* dag = nullptr;       // persistent tile-DAG Cholesky (one kernel per factorisation); overrides plan / la
 };
 

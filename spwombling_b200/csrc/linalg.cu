@@ -44,7 +44,7 @@ using GCfgT = GCfg<32, 64, 2, 3>;
 template <class Cfg>
 __global__ void __launch_bounds__(G_THREADS, Cfg::MINB)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmTask* __restrict__ tasks, MatView C, MatView CT, double alpha) {
+                const GemmTask* __restrict__ tasks, MatView C, MatView CT, double alpha, const GemmSync sy) {
   extern __shared__ __align__(128) unsigned char gsm[];
   double* pipe = reinterpret_cast<double*>(gsm);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(gsm + size_t(Cfg::STAGES) * Cfg::STAGE_BYTES);
@@ -59,6 +59,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&empty[s], G_CW);
     }
     mbar_fence_init();
+    if (sy.wait_flag) {                       // operands written by a kernel that is still running (see GemmSync)
+      const unsigned long long t0 = globaltimer();          // give up after 2 s: never hang the device
+      while (ld_acquire(sy.wait_flag) < sy.wait_val && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
+      fence_proxy_async();
+    }
   }
   __syncthreads();
   auto issue = [&](int kt) {   // one thread: wait for the slot, arm the barrier, launch the two tile loads
@@ -163,6 +168,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         CTp[(long long)c * CT.ld + r] = v0;
         if (two) CTp[(long long)(c + 1) * CT.ld + r] = v1;
       }
+    }
+  }
+  if (sy.done_ctr) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(sy.done_ctr, 1);
     }
   }
 }
@@ -431,17 +443,12 @@ void plan_free(LinalgPlan& plan) {
   plan = LinalgPlan();
 }
 
-// A / B operands are described by (view, logical rows, logical cols): elements outside read as zero.
-struct Operand {
-  MatView v;
-  int rows, cols;
-};
 
 // one_per_sm: pad the dynamic shared memory so that only one CTA fits per SM (leaves room for the CTAs of a
 // concurrently running latency-critical kernel)
 template <class Cfg>
 static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C, MatView CT,
-                           double alpha, cudaStream_t st, bool one_per_sm) {
+                           double alpha, cudaStream_t st, bool one_per_sm, const GemmSync& sy) {
   if (count <= 0 || batch <= 0) return SPW_OK;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -462,19 +469,38 @@ static int launch_gemm_cfg(const GemmTask* tasks, int count, int batch, Operand 
     CUtensorMap tmA, tmB;
     SPW_TRY(make_tensor_map(&tmA, a, A.cols, A.rows, nb, G_LDS, Cfg::BM));
     SPW_TRY(make_tensor_map(&tmB, b, B.cols, B.rows, nb, G_LDS, Cfg::BN));
-    gemm_tma_kernel<Cfg><<<dim3(count, nb), G_THREADS, smem, st>>>(tmA, tmB, tasks, c, ct, alpha);
+    gemm_tma_kernel<Cfg><<<dim3(count, nb), G_THREADS, smem, st>>>(tmA, tmB, tasks, c, ct, alpha, sy);
     SPW_LAUNCHED();
   }
   return SPW_OK;
 }
 
-// shape: 0 = L (128 x 128), 1 = M (128 x 64), 3 = T (32 x 64); the task list must have been tiled accordingly
-static int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
-                             MatView CT, double alpha, cudaStream_t st, bool one_per_sm = false) {
+template <class Cfg>
+static int prepare_gemm_cfg() {
+  SPW_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max<size_t>(Cfg::SMEM, 117 * 1024)));
+  cudaFuncAttributes fa;
+  SPW_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<Cfg>));
+  return SPW_OK;
+}
+
+int gemm_prepare(int shape) {
   switch (shape) {
-    case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
-    case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
-    case 3: return launch_gemm_cfg<GCfgT>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm);
+    case 0: return prepare_gemm_cfg<GCfgL>();
+    case 1: return prepare_gemm_cfg<GCfgM>();
+    case 3: return prepare_gemm_cfg<GCfgT>();
+    default: set_error("gemm: unknown tile shape %d", shape); return SPW_ERR_ARG;
+  }
+}
+
+// shape: 0 = L (128 x 128), 1 = M (128 x 64), 3 = T (32 x 64); the task list must have been tiled accordingly
+int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
+                      MatView CT, double alpha, cudaStream_t st, bool one_per_sm, const GemmSync* sync) {
+  const GemmSync sy = sync ? *sync : GemmSync();
+  switch (shape) {
+    case 0: return launch_gemm_cfg<GCfgL>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm, sy);
+    case 1: return launch_gemm_cfg<GCfgM>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm, sy);
+    case 3: return launch_gemm_cfg<GCfgT>(tasks, count, batch, A, B, C, CT, alpha, st, one_per_sm, sy);
     default: set_error("gemm: unknown tile shape %d", shape); return SPW_ERR_ARG;
   }
 }

@@ -28,6 +28,29 @@ struct MatView {        // a batch of row-major matrices
   long long stride;     // doubles between consecutive batch entries
 };
 
+// A / B operands of the task-driven GEMM are described by (view, logical rows, logical cols): elements outside read
+// as zero.
+struct Operand {
+  MatView v;
+  int rows, cols;
+};
+// Optional coupling of a launch with kernels that run at the same time (the persistent diagonal chain of
+// potrf_la.cu): every CTA starts once *wait_flag >= wait_val and adds 1 to *done_ctr after its stores.
+struct GemmSync {
+  const int* wait_flag = nullptr;
+  int wait_val = 0;
+  int* done_ctr = nullptr;
+};
+// Launches tasks[0 .. count) for every batch entry: C (+)= alpha * A_tile * B_tile^T.  shape: 0 = 128 x 128 tiles
+// (1 CTA/SM), 1 = 128 x 64 (2 CTA/SM), 3 = 32 x 64 (3 CTA/SM); the task list must have been tiled accordingly.
+// one_per_sm pads the shared memory so that a single CTA fits per SM (room for concurrent latency-critical kernels).
+int launch_gemm_tasks(int shape, const GemmTask* tasks, int count, int batch, Operand A, Operand B, MatView C,
+                      MatView CT, double alpha, cudaStream_t st, bool one_per_sm = false, const GemmSync* sync = nullptr);
+
+// Loads the kernel of a tile shape (a first-use module load synchronises the device: callers that keep a kernel
+// resident while they launch others call this first).
+int gemm_prepare(int shape);
+
 // Schedule for one matrix order n: per-step slices into one device-resident task array.
 struct ChunkRange { int begin, count; };
 struct LinalgPlan {

@@ -1,0 +1,517 @@
+// Single-matrix blocked Cholesky (order n, NB = 64) with a two-step look-ahead, for the strictly sequential chain of
+// hlmBayes_sp (chol() of R/hlmBayes_sp.R:114,140,181: one matrix of order N + 1 per proposal).  EXPERIMENTAL, opt-in
+// with SPW_LA=1: 3-6 % faster than the shadow schedule of potrf_batched for orders 2000 .. 7000 (2.36 against 2.47 ms
+// at 5000), not enough to make a persistent kernel that spins on flags the default.
+//
+// The right-looking schedule has the critical path  diag(j) -> panel(j) -> update(j) -> diag(j+1).  Here the chain
+// of diagonal blocks is ONE single-CTA kernel that stays resident for the whole factorisation and finishes its own
+// row block itself, so that step j depends on step j-1 and on work launched TWO steps earlier only:
+//
+//   D(j)      tile (j, j-1) -= L(j, j-2) L(j-1, j-2)^T          (source j-2, the last one missing)
+//             L(j, j-1) = tile (j, j-1) * Dinv(j-1)^T           (panel product of its own row)
+//             tile (j, j) -= L(j, j-1) L(j, j-1)^T              (source j-1)
+//             factor and invert tile (j, j)                     (the sweep of diag_factor.cuh)
+//             starts when LLS(j) has finished (a counter its CTAs increment), publishes d_done = j + 1.
+//   side stream (highest priority), per step j:
+//     PANEL2(j)  L(r, j) = (A(r, j) - L(r, j-1) L(j, j-1)^T) Dinv(j)^T, rows >= j+2; its CTAs wait for d_done > j
+//     LLS(j+2)   sources s0 .. j -> column j+2, rows >= j+2, ONE product with K = 64 (j + 1 - s0)  (left-looking over
+//                the sources the bulk updates have not covered: s0 = 4 (c / 4 - 1) for target column c)
+//   bulk streams (lowest priority; target outer block cb on stream cb mod 3), when the panels of outer block m
+//   (256 columns) are final, nearest target first:
+//     G(m, cb), cb = m+2 .. m+H-1        K = 256; G(m, m+2) is awaited by the first LLS into block m+2, 3 steps later
+//     LL(0..m -> m+H)                    one product with K = 256 (m+1) when block m+H enters the horizon (SPW_LA_HORIZON;
+//                                        default: no horizon, every update is a G)
+//
+// Every product but PANEL2 is a task list of the TMA-fed DMMA kernel of linalg.cu.  Stream order, three events per
+// outer block and the two flags are the only synchronisation; the pattern forks from and joins the caller's stream,
+// so it can be captured into a CUDA graph.  Deterministic: every tile receives its updates in a fixed order.
+//
+// What the per-step trace (SPW_LA_TRACE=1, tools/la_trace.py) shows at order 5001: a chain step takes 20.1 us
+// (1.5 loads + 5.2 look-ahead products at one SM's 250 GFLOP/s + 12.8 sweep + 0.6 hand-over); the first ~30 steps
+// are bound by the machine (per-step work > 20 us x 30 TFLOP/s; the trace shows ~30 TFLOP/s sustained there), the
+// last ~50 by the chain: 32 GFLOP / 30 TFLOP/s + 49 x 20 us = 2.05 ms is the floor of this design, 2.36 ms measured.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "potrf_la.cuh"
+#include "diag_factor.cuh"
+#include "tile64.cuh"
+
+namespace spw {
+
+namespace {
+constexpr int XP_DOUBLES = DIAG_LOW * DIAG_TS;    // packed inverse of one diagonal block
+struct LaSmem {
+  DiagSmem diag;                 // the 64 x 68 tile (j, j-1) lives over diag.Lt | diag.Xt until the sweep starts
+  double bufB[C_TILE];           // L(j-1, j-2), then the updated tile (j, j) = input of the sweep
+  double xp[XP_DOUBLES];         // packed inverse of diagonal block j-1
+};
+static_assert(2 * DIAG_LOW * DIAG_TS >= C_TILE, "tile (j, j-1) must fit over Lt | Xt");
+static_assert(offsetof(DiagSmem, Xt) == sizeof(double) * DIAG_LOW * DIAG_TS, "Lt and Xt must be contiguous");
+}  // namespace
+
+// One step of the chain: the look-ahead products of row block j and the sweep of diagonal block j.  sm.xp holds the
+// packed inverse of diagonal block j-1 on entry and that of block j on exit.
+__device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, double* __restrict__ dinv, int nblk,
+                                        int* __restrict__ status) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const MatView none{nullptr, 0, 0};
+  const int r0 = j * NB, bs = min(NB, n - r0);
+  const long long ld = L.ld;
+  double* Lg = L.p;
+  if (j > 0) {
+    double* T = sm.diag.Lt;
+    const bool two = j >= 2;
+    const double* a1 = Lg + (long long)r0 * ld + (j - 1) * NB;            // tile (j, j-1)
+    const double* b1 = Lg + (long long)(r0 - NB) * ld + (j - 2) * NB;     // L(j-1, j-2)
+    const double* x1p = Lg + (long long)r0 * ld + (j - 2) * NB;           // L(j, j-2)
+    const double* sp = Lg + (long long)r0 * ld + r0;                      // tile (j, j)
+    // ---- every global load of the step is issued before the first one is used ----
+    constexpr int NV = NB * NB / 2, PT = (NV + DIAG_THREADS - 1) / DIAG_THREADS;
+    double2 vt[PT], vb[PT];
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      const int e = tid + i * DIAG_THREADS, r = e >> 5, c = (e & 31) * 2;
+      vt[i] = vb[i] = make_double2(0.0, 0.0);
+      if (e < NV) {
+        if (r < bs) vt[i] = __ldcg(reinterpret_cast<const double2*>(a1 + (long long)r * ld + c));
+        if (two) vb[i] = __ldcg(reinterpret_cast<const double2*>(b1 + (long long)r * ld + c));
+      }
+    }
+    double x1[16];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) x1[k4] = 0.0;
+    if (two && warp < 8 && 8 * warp + g < bs) {
+#pragma unroll
+      for (int k4 = 0; k4 < 16; ++k4) x1[k4] = __ldcg(x1p + (long long)(8 * warp + g) * ld + 4 * k4 + q);
+    }
+    double2 sc[3];
+    int smt[3], snt[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      int t = warp + 12 * i, mt = 0;
+      while (t > mt) { t -= mt + 1; ++mt; }
+      smt[i] = mt; snt[i] = t;
+      const int row = 8 * mt + g, col = 8 * t + 2 * q;
+      sc[i] = make_double2(0.0, 0.0);
+      if (row < bs) {
+        if (col + 1 < bs) sc[i] = __ldcg(reinterpret_cast<const double2*>(sp + (long long)row * ld + col));
+        else if (col < bs) sc[i].x = __ldcg(sp + (long long)row * ld + col);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      const int e = tid + i * DIAG_THREADS, r = e >> 5, c = (e & 31) * 2;
+      if (e < NV) {
+        *reinterpret_cast<double2*>(T + r * C_LD + c) = vt[i];
+        *reinterpret_cast<double2*>(sm.bufB + r * C_LD + c) = vb[i];
+      }
+    }
+    __syncthreads();
+    if (warp < 8) {
+      if (two) {
+        // ---- rows 8 warp .. 8 warp + 7 of tile (j, j-1) -= L(j, j-2) L(j-1, j-2)^T ----
+        double acc[8][2];
+        double* crow = T + (8 * warp + g) * C_LD + 2 * q;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const double2 v = *reinterpret_cast<const double2*>(crow + 8 * nt);
+          acc[nt][0] = v.x; acc[nt][1] = v.y;
+        }
+        const double* brow = sm.bufB + g * C_LD + q;
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+          const double a = -x1[k4];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], a, brow[8 * nt * C_LD + 4 * k4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(crow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+        __syncwarp();
+      }
+      // ---- L(j, j-1) = tile * Dinv(j-1)^T: in place and to global memory ----
+      chain_panel_rows(T, sm.xp, warp, Lg + (long long)r0 * ld + (j - 1) * NB, ld, bs, NB, lane);
+    }
+    __syncthreads();
+    // ---- tile (j, j) -= L(j, j-1) L(j, j-1)^T: 36 lower 8 x 8 tiles, three per warp; the result feeds the sweep ----
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double2 v = sc[i];
+      const double* arow = T + (8 * smt[i] + g) * C_LD + q;
+      const double* brow = T + (8 * snt[i] + g) * C_LD + q;
+#pragma unroll
+      for (int k4 = 0; k4 < 16; ++k4) dmma884(v.x, v.y, -arow[4 * k4], brow[4 * k4]);
+      *reinterpret_cast<double2*>(sm.bufB + (8 * smt[i] + g) * C_LD + 8 * snt[i] + 2 * q) = v;
+    }
+    __syncthreads();
+    diag_factor_block<false, false, true>(sm.diag, L, 0, j, n, dinv, nblk, none, 0, status, nullptr, sm.bufB);
+  } else {
+    diag_factor_block<true>(sm.diag, L, 0, j, n, dinv, nblk, none, 0, status, nullptr);
+  }
+  for (int e = tid; e < XP_DOUBLES / 2; e += DIAG_THREADS)
+    reinterpret_cast<double2*>(sm.xp)[e] = reinterpret_cast<const double2*>(sm.diag.Xt)[e];
+}
+
+// The whole chain of diagonal blocks as ONE single-CTA kernel that stays resident for the factorisation (its SM
+// slot and shared memory are never contended).  Coupling with the products the side stream launches meanwhile:
+//   * step j starts once the LLS(j) launch has finished (every CTA of it adds 1 to lls_done[j]);
+//   * d_done = j + 1 is published once the outputs of step j are in global memory; the CTAs of UCOL(j-1) / PANEL(j)
+//     wait for it (GemmSync of linalg.cu).
+// A wait that lasts longer than two seconds gives up (status LA_STALLED): a scheduling accident must not hang the
+// device or go unnoticed.
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __restrict__ status,
+                  int* __restrict__ flags, const int* __restrict__ expect, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  LaSmem& sm = *reinterpret_cast<LaSmem*>(lsm);
+  const int tid = threadIdx.x;
+  bool stalled = false;                    // thread 0: a wait has given up; the result is void, do not wait again
+  for (int j = 0; j < nblk; ++j) {
+    if (trace && tid == 0) trace[3 * j] = globaltimer();
+    if (tid == 0 && j >= 2 && !stalled) {
+      const int want = expect[j];
+      const unsigned long long t0 = globaltimer();
+      while (ld_acquire(flags + 1 + j) < want) {
+        if (globaltimer() - t0 > 2000000000ull) {
+          atomicExch(status, LA_STALLED);
+          stalled = true;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (trace && tid == 0) trace[3 * j + 1] = globaltimer();
+    la_step(sm, L, j, n, dinv, nblk, status);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(flags, j + 1);
+      if (trace) trace[3 * j + 2] = globaltimer();
+    }
+  }
+}
+
+
+// PANEL(j) with the last missing update folded in, for the rows below the diagonal kernels' band (row r >= rbeg):
+//   L(r, j) = (A(r, j) - L(r, j-1) L(j, j-1)^T) Dinv(j)^T
+// One CTA per 64 rows, 8 warps x 8 rows, both products on the tensor pipe out of shared memory, one round of global
+// loads.  Replaces two launches of the generic tile kernel (each ~9 us of latency chain for K = 64) on the side
+// stream.  The CTAs start once the chain kernel has published step j (d_done >= j + 1).
+struct Panel2Smem {
+  double T[C_TILE / 2];  // A(r, j), up to 32 rows -> updated rows
+  double B[C_TILE];      // L(j, j-1), then Dinv(j): 52 KB per CTA, so that it fits beside resident bulk CTAs
+};
+
+template <int NW>     // warps per CTA = 8-row groups (4: 32 rows per CTA)
+__global__ void __launch_bounds__(32 * NW, 2)
+panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restrict__ dinv, const int* __restrict__ d_done,
+              int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  Panel2Smem& sm = *reinterpret_cast<Panel2Smem*>(psm);
+  constexpr int NT = 32 * NW, RB = 8 * NW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int r0 = rbeg + blockIdx.x * RB, nr = min(RB, rows - r0), bs = min(NB, n - j * NB);
+  const long long ld = L.ld;
+  if (d_done) {
+    if (tid == 0) {
+      const unsigned long long t0 = globaltimer();
+      while (ld_acquire(d_done) < j + 1) {
+        if (globaltimer() - t0 > 2000000000ull || ld_relaxed(status) == LA_STALLED) {
+          atomicExch(status, LA_STALLED);
+          break;
+        }
+        __nanosleep(40);
+      }
+    }
+    __syncthreads();
+  }
+  const bool upd = j >= 1;
+  const double* a = L.p + (long long)r0 * ld + j * NB;                     // A(r, j)
+  const double* x1p = L.p + (long long)r0 * ld + (j - 1) * NB;             // L(r, j-1)
+  const double* b1 = L.p + (long long)(j * NB) * ld + (j - 1) * NB;        // L(j, j-1)
+  const double* dv = dinv + (long long)j * NB * NB;                        // Dinv(j), ld = NB, zero outside bs x bs
+  constexpr int PA = RB * 32 / NT, PB = NB * 32 / NT;                      // double2 per thread: own rows / 64 x 64 operands
+  double2 vt[PA], vb[PB], vd[PB];
+#pragma unroll
+  for (int i = 0; i < PA; ++i) {
+    const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+    vt[i] = make_double2(0.0, 0.0);
+    if (r < nr) {
+      if (c + 1 < bs) vt[i] = __ldcg(reinterpret_cast<const double2*>(a + (long long)r * ld + c));
+      else if (c < bs) vt[i].x = __ldcg(a + (long long)r * ld + c);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PB; ++i) {
+    const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+    vb[i] = make_double2(0.0, 0.0);
+    if (upd && r < bs) vb[i] = __ldcg(reinterpret_cast<const double2*>(b1 + (long long)r * ld + c));
+    vd[i] = __ldcg(reinterpret_cast<const double2*>(dv + r * NB + c));
+  }
+  double x1[16];
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) x1[k4] = 0.0;
+  if (upd && 8 * warp + g < nr) {
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) x1[k4] = __ldcg(x1p + (long long)(8 * warp + g) * ld + 4 * k4 + q);
+  }
+#pragma unroll
+  for (int i = 0; i < PA; ++i) {
+    const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(sm.T + r * C_LD + c) = vt[i];
+  }
+#pragma unroll
+  for (int i = 0; i < PB; ++i) {
+    const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(sm.B + r * C_LD + c) = upd ? vb[i] : vd[i];
+  }
+  __syncthreads();
+  double acc[8][2];
+  double* crow = sm.T + (8 * warp + g) * C_LD + 2 * q;
+  if (upd) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const double2 v = *reinterpret_cast<const double2*>(crow + 8 * nt);
+      acc[nt][0] = v.x; acc[nt][1] = v.y;
+    }
+    const double* brow = sm.B + g * C_LD + q;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const double av = -x1[k4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], av, brow[8 * nt * C_LD + 4 * k4]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(crow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+    __syncthreads();                     // every warp is done with L(j, j-1): the buffer takes Dinv(j)
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+      *reinterpret_cast<double2*>(sm.B + r * C_LD + c) = vd[i];
+    }
+    __syncthreads();
+  }
+  // rows 8 warp .. 8 warp + 7 times Dinv(j)^T (lower triangular: k <= column)
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  {
+    const double* arow = sm.T + (8 * warp + g) * C_LD + q;
+    const double* brow = sm.B + g * C_LD + q;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const double av = arow[4 * k4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        if (nt >= (k4 >> 1)) dmma884(acc[nt][0], acc[nt][1], av, brow[8 * nt * C_LD + 4 * k4]);
+    }
+  }
+  const int r = 8 * warp + g;
+  if (r < nr) {
+    double* dst = L.p + (long long)(r0 + r) * ld + j * NB;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = 8 * nt + 2 * q;
+      if (c + 1 < bs) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[nt][0], acc[nt][1]);
+      else if (c < bs) dst[c] = acc[nt][0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+static GemmTask la_blank() {
+  GemmTask t;
+  memset(&t, 0, sizeof(t));
+  return t;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static const int SMALL_M = 32, SMALL_N = 64;     // tile shape 3 of linalg.cu: the latency-critical products
+
+int la_plan_build(LaPlan& plan, int n, int extra_rows) {
+  la_plan_free(plan);
+  plan.n = n;
+  plan.rows = n + extra_rows;
+  plan.nblk = ceil_div(n, NB);
+  plan.nouter = ceil_div(n, OUTER_W);
+  plan.horizon = std::max(3, env_int("SPW_LA_HORIZON", 1 << 20));
+  const int per = OUTER_W / NB, H = plan.horizon, rows = plan.rows, nblk = plan.nblk;
+  std::vector<GemmTask> tasks;
+  const int BULK_M = SMALL_M, BULK_N = SMALL_N;
+  plan.lls.assign(nblk, ChunkRange{0, 0});
+  auto bsz = [&](int c) { return std::min(NB, n - c * NB); };
+  // LLS(c): sources s0(c) .. c-2 -> column c, rows >= c
+  for (int c = 2; c < nblk; ++c) {
+    const int s0 = per * std::max(0, c / per - 1), K = NB * (c - 1 - s0);
+    plan.lls[c].begin = (int)tasks.size();
+    for (int r = c * NB; r < rows; r += SMALL_M) {
+      GemmTask t = la_blank();
+      t.a_row = r; t.a_col = s0 * NB;
+      t.b_row = c * NB; t.b_col = s0 * NB;
+      t.c_row = r; t.c_col = c * NB;
+      t.m = std::min(SMALL_M, rows - r); t.n = bsz(c); t.k = K;
+      t.flags = GT_ACCUM | GT_STORE;
+      tasks.push_back(t);
+    }
+    plan.lls[c].count = (int)tasks.size() - plan.lls[c].begin;
+  }
+  // bulk updates of outer block cb by the source outer blocks [m0, m1]: lower tiles, column by column
+  auto bulk = [&](int m0, int m1, int cb) {
+    const int c_begin = cb * OUTER_W, c_end = std::min(c_begin + OUTER_W, n);
+    for (int c = c_begin; c < c_end; c += BULK_N)
+      for (int r = c_begin; r < rows; r += BULK_M) {
+        const int m = std::min(BULK_M, rows - r);
+        if (c > r + m - 1) continue;
+        GemmTask t = la_blank();
+        t.a_row = r; t.a_col = m0 * OUTER_W;
+        t.b_row = c; t.b_col = m0 * OUTER_W;
+        t.c_row = r; t.c_col = c;
+        t.m = m; t.n = std::min(BULK_N, n - c); t.k = (m1 - m0 + 1) * OUTER_W;
+        t.flags = GT_ACCUM | GT_STORE;
+        tasks.push_back(t);
+      }
+  };
+  plan.bulk.assign(plan.nouter, {});
+  for (int m = 0; m < plan.nouter; ++m)
+    for (int cb = m + 2; cb <= m + H && cb < plan.nouter; ++cb) {
+      LaPlan::BulkLaunch bl;
+      bl.cb = cb;
+      bl.tasks.begin = (int)tasks.size();
+      if (cb == m + H) bulk(0, m, cb);        // outer block cb enters the horizon: every source block so far at once
+      else bulk(m, m, cb);
+      bl.tasks.count = (int)tasks.size() - bl.tasks.begin;
+      if (bl.tasks.count > 0) plan.bulk[m].push_back(bl);
+    }
+  plan.n_tasks = (int)tasks.size();
+  if (plan.n_tasks > 0) {
+    SPW_CUDA(cudaMalloc(&plan.d_tasks, sizeof(GemmTask) * tasks.size()));
+    SPW_CUDA(cudaMemcpy(plan.d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice));
+  }
+  std::vector<int> expect(nblk, 0);
+  for (int c = 0; c < nblk; ++c) expect[c] = plan.lls[c].count;
+  SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(nblk + 1)));
+  SPW_CUDA(cudaMalloc(&plan.d_expect, sizeof(int) * (size_t)nblk));
+  if (env_int("SPW_LA_TRACE", 0)) {
+    SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 3 * (size_t)nblk));
+    SPW_CUDA(cudaMemset(plan.d_trace, 0, sizeof(unsigned long long) * 3 * (size_t)nblk));
+  }
+  SPW_CUDA(cudaMemcpy(plan.d_expect, expect.data(), sizeof(int) * (size_t)nblk, cudaMemcpyHostToDevice));
+  return SPW_OK;
+}
+
+void la_plan_free(LaPlan& plan) {
+  if (plan.d_tasks) cudaFree(plan.d_tasks);
+  if (plan.d_flags) cudaFree(plan.d_flags);
+  if (plan.d_expect) cudaFree(plan.d_expect);
+  if (plan.d_trace) cudaFree(plan.d_trace);
+  plan = LaPlan();
+}
+
+int la_trace_read(const LaPlan& plan, std::vector<unsigned long long>& out) {
+  out.clear();
+  if (!plan.d_trace) return SPW_OK;
+  out.resize(3 * (size_t)plan.nblk);
+  SPW_CUDA(cudaMemcpy(out.data(), plan.d_trace, sizeof(unsigned long long) * out.size(), cudaMemcpyDeviceToHost));
+  return SPW_OK;
+}
+
+int la_streams_reserve(LaStreams& s, int nblk) {
+  if (!s.side) {
+    int lo = 0, hi = 0;
+    SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SPW_CUDA(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < LaStreams::NBULK; ++i) {
+      SPW_CUDA(cudaStreamCreateWithPriority(&s.bulk[i], cudaStreamNonBlocking, lo));
+      SPW_CUDA(cudaEventCreateWithFlags(&s.ev_bjoin[i], cudaEventDisableTiming));
+    }
+    SPW_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+  }
+  auto grow = [&](std::vector<cudaEvent_t>& v, size_t need) -> int {
+    while (v.size() < need) {
+      cudaEvent_t e;
+      SPW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      v.push_back(e);
+    }
+    return SPW_OK;
+  };
+  SPW_TRY(grow(s.ev_p, nblk / (OUTER_W / NB) + 2));
+  SPW_TRY(grow(s.ev_g, nblk / (OUTER_W / NB) + 2));
+  return SPW_OK;
+}
+
+int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, int* status, cudaStream_t st) {
+  const int nblk = plan.nblk, per = OUTER_W / NB;
+  SPW_TRY(la_streams_reserve(s, nblk));
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  SPW_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    SPW_CUDA(cudaFuncSetAttribute(diag_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaSmem)));
+    SPW_CUDA(cudaFuncSetAttribute(panel2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Panel2Smem)));
+    // every kernel the side streams launch must be loaded before the chain kernel starts: a first-use module load
+    // waits for the device to drain, which the resident chain kernel (waiting for those very launches) never lets
+    // happen
+    cudaFuncAttributes fa;
+    SPW_CUDA(cudaFuncGetAttributes(&fa, panel2_kernel<4>));
+    SPW_TRY(gemm_prepare(3));
+    attr_set[dev & 63] = true;
+  }
+  MatView none{nullptr, 0, 0};
+  Operand opL{L, plan.rows, plan.n};
+  auto run = [&](const ChunkRange& r, cudaStream_t q, const GemmSync* sy) -> int {
+    if (r.count == 0) return SPW_OK;
+    return launch_gemm_tasks(3, plan.d_tasks + r.begin, r.count, 1, opL, opL, L, none, -1.0, q, false, sy);
+  };
+  int* d_done = plan.d_flags;
+  int* lls_done = plan.d_flags + 1;
+  SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(nblk + 1), st));
+  // fork: the side and bulk streams join the caller's stream (and its graph capture)
+  SPW_CUDA(cudaEventRecord(s.ev_fork, st));
+  SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
+  for (int i = 0; i < LaStreams::NBULK; ++i) SPW_CUDA(cudaStreamWaitEvent(s.bulk[i], s.ev_fork, 0));
+  diag_chain_kernel<<<1, DIAG_THREADS, sizeof(LaSmem), st>>>(L, plan.n, dinv, nblk, status, plan.d_flags, plan.d_expect,
+                                                             plan.d_trace);
+  SPW_LAUNCHED();
+  for (int j = 0; j < nblk; ++j) {
+    const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
+    if (nrow > 0) {
+      panel2_kernel<4><<<ceil_div(nrow, 32), 128, sizeof(Panel2Smem), s.side>>>(L, j, plan.n, plan.rows, rbeg, dinv, d_done,
+                                                                                 status);
+      SPW_LAUNCHED();
+    }
+    const int m = j / per;
+    if ((j + 1) % per == 0 && !plan.bulk[m].empty()) {       // the panels of outer block m are final
+      SPW_CUDA(cudaEventRecord(s.ev_p[m], s.side));
+      for (const auto& bl : plan.bulk[m]) {
+        cudaStream_t q = s.bulk[bl.cb % LaStreams::NBULK];
+        SPW_CUDA(cudaStreamWaitEvent(q, s.ev_p[m], 0));
+        SPW_TRY(run(bl.tasks, q, nullptr));
+        SPW_CUDA(cudaEventRecord(s.ev_g[bl.cb], q));
+      }
+    }
+    const int c = j + 2;
+    if (c < nblk) {
+      // the first LLS into outer block cb waits for the last bulk update into it, G(cb - 2, cb)
+      if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_g[c / per], 0));
+      GemmSync done;
+      done.done_ctr = lls_done + c;
+      SPW_TRY(run(plan.lls[c], s.side, &done));
+    }
+  }
+  // join
+  SPW_CUDA(cudaEventRecord(s.ev_join, s.side));
+  SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
+  for (int i = 0; i < LaStreams::NBULK; ++i) {
+    SPW_CUDA(cudaEventRecord(s.ev_bjoin[i], s.bulk[i]));
+    SPW_CUDA(cudaStreamWaitEvent(st, s.ev_bjoin[i], 0));
+  }
+  return SPW_OK;
+}
+
+}  // namespace spw

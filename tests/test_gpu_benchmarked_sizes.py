@@ -189,7 +189,7 @@ sys.path.insert(0, %(root)r)
 import spwombling_b200 as spw
 from oracle.hlm import hlm_bayes_sp, r_chol
 import oracle
-for n in (257, 300, 1100, 1985):
+for n in %(orders)r:
     rng = np.random.Generator(np.random.Philox(n))
     coords = rng.random((n, 2))
     A = oracle.cov_matern1(oracle.dist_matrix(coords), 8.0, 2.0) + 0.5 * np.eye(n)
@@ -197,7 +197,7 @@ for n in (257, 300, 1100, 1985):
     Uo = r_chol(A)
     assert np.max(np.abs(U - Uo)) / np.max(np.abs(Uo)) < 1e-11, n
     U2, _ = spw.chol(A)
-    assert np.array_equal(U, U2), "the persistent kernel must be deterministic"
+    assert np.array_equal(U, U2), "the schedule must be deterministic"
 n, niter = 1100, 4
 rng = np.random.Generator(np.random.Philox(77))
 coords = rng.random((n, 2))
@@ -214,14 +214,20 @@ print("ok")
 """
 
 
-def test_persistent_tile_dag_cholesky_against_oracle():
-    """The opt-in persistent single-matrix Cholesky (SPW_DAG=1; the switch is read per call but plans are cached per
-    process, hence the subprocess): ragged orders, the appended y row of the hlm system, run-to-run determinism."""
+@pytest.mark.parametrize("switches, orders", [
+    ({"SPW_DAG": "1", "SPW_DAG_MIN": "200"}, (257, 300, 1100, 1985)),
+    ({"SPW_LA": "1", "SPW_LA_MIN": "60"}, (65, 130, 257, 300, 513, 1100, 1985)),
+    ({"SPW_LA": "1", "SPW_LA_MIN": "60", "SPW_LA_HORIZON": "3"}, (1100, 1985)),
+], ids=["tile_dag", "lookahead", "lookahead_horizon3"])
+def test_opt_in_single_matrix_cholesky_schedules_against_oracle(switches, orders):
+    """The opt-in single-matrix Cholesky schedules -- the persistent tile-DAG kernel (SPW_DAG=1) and the look-ahead
+    schedule with a resident diagonal chain (SPW_LA=1).  The switches are read per call but plans are cached per
+    process, hence the subprocess: ragged orders, the appended y row of the hlm system, run-to-run determinism."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SPW_DAG="1", SPW_DAG_MIN="200")
-    res = subprocess.run([sys.executable, "-c", _DAG_SCRIPT % {"root": root}], env=env, capture_output=True, text=True,
-                         timeout=600)
+    env = dict(os.environ, **switches)
+    res = subprocess.run([sys.executable, "-c", _DAG_SCRIPT % {"root": root, "orders": tuple(orders)}], env=env,
+                         capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-4000:]

@@ -10,6 +10,8 @@ echo "launch list c5 rc=$?"
 $CMD1 > gpurun_out/plain1.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:gradient_tma -s 3 -c 1 -f -o gpurun_out/r02_prof_main_c5 $CMD1 > gpurun_out/ncu2.log 2>&1
 echo "full main rc=$?"
+# ncu replays kernels one at a time: the look-ahead schedule (kernels that wait for each other) cannot run under it
+export SPW_LA=0
 CMD2="python tools/hlm_bench.py 5000 2 matern2 1"
 $CMD2 > gpurun_out/plain2.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 7000 --csv --log-file gpurun_out/r02_launches_hlm5000.csv $CMD2 > gpurun_out/ncu3.log 2>&1
