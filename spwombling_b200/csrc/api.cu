@@ -764,8 +764,9 @@ __global__ void debug_fill_kernel(double* __restrict__ a, long long ld, int rows
   a[(long long)i * ld + j] = (i < n ? exp(-0.02 * d) + (d == 0 ? 1.0 : 0.0) : 1.0);
 }
 
-// diagnostic (SPW_LA_TRACE=1): per diagonal step of the last look-ahead factorisation of order n: wait begins, step
-// begins, step published (globaltimer ns).  Returns the words written.
+// diagnostic (SPW_LA_TRACE=1): 8 words per diagonal step of the last look-ahead factorisation of order n (globaltimer
+// ns): chain wait begins, step begins, step published, PANEL2(j) first start / last end, LLS(j) first start / last end.
+// Returns the words written.
 long long spw_debug_la_trace(int n, int extra, unsigned long long* out, long long cap_words) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

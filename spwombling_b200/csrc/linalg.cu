@@ -54,6 +54,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nkt = (t.k + G_BK - 1) / G_BK;
   if (tid == 0) {
+    if (sy.stamp) atomicMin(sy.stamp, globaltimer());
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], G_CW);
@@ -175,6 +176,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0) {
       __threadfence();
       atomicAdd(sy.done_ctr, 1);
+      if (sy.stamp) atomicMax(sy.stamp + 1, globaltimer());
     }
   }
 }

@@ -40,6 +40,7 @@ struct GemmSync {
   const int* wait_flag = nullptr;
   int wait_val = 0;
   int* done_ctr = nullptr;
+  unsigned long long* stamp = nullptr;   // optional trace: stamp[0] = earliest CTA start, stamp[1] = latest CTA end (ns)
 };
 // Launches tasks[0 .. count) for every batch entry: C (+)= alpha * A_tile * B_tile^T.  shape: 0 = 128 x 128 tiles
 // (1 CTA/SM), 1 = 128 x 64 (2 CTA/SM), 3 = 32 x 64 (3 CTA/SM); the task list must have been tiled accordingly.

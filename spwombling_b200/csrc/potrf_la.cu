@@ -1,7 +1,8 @@
 // Single-matrix blocked Cholesky (order n, NB = 64) with a two-step look-ahead, for the strictly sequential chain of
-// hlmBayes_sp (chol() of R/hlmBayes_sp.R:114,140,181: one matrix of order N + 1 per proposal).  EXPERIMENTAL, opt-in
-// with SPW_LA=1: 3-6 % faster than the shadow schedule of potrf_batched for orders 2000 .. 7000 (2.36 against 2.47 ms
-// at 5000), not enough to make a persistent kernel that spins on flags the default.
+// hlmBayes_sp (chol() of R/hlmBayes_sp.R:114,140,181: one matrix of order N + 1 per proposal).
+// DEFAULT from order 2048 on (SPW_LA=0 disables it, SPW_LA_MIN moves the threshold): 4-7 % faster than the shadow
+// schedule of potrf_batched for orders 2000 .. 7000 (2.30-2.36 against 2.45-2.47 ms at 5000; hlmBayes_sp at N = 5000:
+// 136 against 125 iterations/s).
 //
 // The right-looking schedule has the critical path  diag(j) -> panel(j) -> update(j) -> diag(j+1).  Here the chain
 // of diagonal blocks is ONE single-CTA kernel that stays resident for the whole factorisation and finishes its own
@@ -27,9 +28,16 @@
 // so it can be captured into a CUDA graph.  Deterministic: every tile receives its updates in a fixed order.
 //
 // What the per-step trace (SPW_LA_TRACE=1, tools/la_trace.py) shows at order 5001: a chain step takes 20.1 us
-// (1.5 loads + 5.2 look-ahead products at one SM's 250 GFLOP/s + 12.8 sweep + 0.6 hand-over); the first ~30 steps
-// are bound by the machine (per-step work > 20 us x 30 TFLOP/s; the trace shows ~30 TFLOP/s sustained there), the
-// last ~50 by the chain: 32 GFLOP / 30 TFLOP/s + 49 x 20 us = 2.05 ms is the floor of this design, 2.36 ms measured.
+// (1.5 loads + 5.2 look-ahead products at one SM's 250 GFLOP/s + 12.8 sweep + 0.6 hand-over) and the side chain of a
+// step (PANEL2 6.5 us + LLS 12 us) almost as long.  The first ~30 steps are bound by the machine (per-step work >
+// 20 us x 30 TFLOP/s, which is what the trace shows sustained there), the last ~50 by the chain: 32 GFLOP / 30 TFLOP/s
+// + 49 x 20 us = 2.05 ms is the floor of this design; 2.3 ms measured.  The difference sits in outer blocks 5 .. 12:
+// while the ~3000 CTAs of a bulk update wait for SM slots, a kernel launched on the side stream gets its first CTA
+// running 15-27 us late (with a free slot on every SM and with the highest stream priority alike), twice per step.
+// Tried against it, all slower: two bulk CTAs per SM (shared-memory padding), bulk launches of 296 / 441 CTAs that
+// stay resident and walk the task list (the side kernels then start at once, but two bulk CTAs per SM sustain
+// only ~17 TFLOP/s and with three the side CTAs get a quarter of their SM: PANEL2 50 us, LLS 60 us), 128 x 64 bulk
+// tiles, left-looking horizons 3 .. 8, four-stage rings for LLS.  There is no priority inside an SM.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -167,7 +175,7 @@ diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __
   const int tid = threadIdx.x;
   bool stalled = false;                    // thread 0: a wait has given up; the result is void, do not wait again
   for (int j = 0; j < nblk; ++j) {
-    if (trace && tid == 0) trace[3 * j] = globaltimer();
+    if (trace && tid == 0) trace[8 * j] = globaltimer();
     if (tid == 0 && j >= 2 && !stalled) {
       const int want = expect[j];
       const unsigned long long t0 = globaltimer();
@@ -180,13 +188,13 @@ diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __
       }
     }
     __syncthreads();
-    if (trace && tid == 0) trace[3 * j + 1] = globaltimer();
+    if (trace && tid == 0) trace[8 * j + 1] = globaltimer();
     la_step(sm, L, j, n, dinv, nblk, status);
     __syncthreads();
     if (tid == 0) {
       __threadfence();
       st_release(flags, j + 1);
-      if (trace) trace[3 * j + 2] = globaltimer();
+      if (trace) trace[8 * j + 2] = globaltimer();
     }
   }
 }
@@ -203,9 +211,9 @@ struct Panel2Smem {
 };
 
 template <int NW>     // warps per CTA = 8-row groups (4: 32 rows per CTA)
-__global__ void __launch_bounds__(32 * NW, 2)
+__global__ void __launch_bounds__(32 * NW, 3)    // <= 168 registers: a CTA fits the slot a 32 x 64 GEMM CTA frees
 panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restrict__ dinv, const int* __restrict__ d_done,
-              int* __restrict__ status) {
+              int* __restrict__ status, unsigned long long* __restrict__ stamp) {
   extern __shared__ __align__(16) unsigned char psm[];
   Panel2Smem& sm = *reinterpret_cast<Panel2Smem*>(psm);
   constexpr int NT = 32 * NW, RB = 8 * NW;
@@ -225,6 +233,7 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
     }
     __syncthreads();
   }
+  if (stamp && tid == 0) atomicMin(stamp, globaltimer());
   const bool upd = j >= 1;
   const double* a = L.p + (long long)r0 * ld + j * NB;                     // A(r, j)
   const double* x1p = L.p + (long long)r0 * ld + (j - 1) * NB;             // L(r, j-1)
@@ -315,6 +324,10 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
       else if (c < bs) dst[c] = acc[nt][0];
     }
   }
+  if (stamp) {
+    __syncthreads();
+    if (tid == 0) atomicMax(stamp + 1, globaltimer());
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -397,8 +410,7 @@ int la_plan_build(LaPlan& plan, int n, int extra_rows) {
   SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(nblk + 1)));
   SPW_CUDA(cudaMalloc(&plan.d_expect, sizeof(int) * (size_t)nblk));
   if (env_int("SPW_LA_TRACE", 0)) {
-    SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 3 * (size_t)nblk));
-    SPW_CUDA(cudaMemset(plan.d_trace, 0, sizeof(unsigned long long) * 3 * (size_t)nblk));
+    SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 8 * (size_t)nblk));
   }
   SPW_CUDA(cudaMemcpy(plan.d_expect, expect.data(), sizeof(int) * (size_t)nblk, cudaMemcpyHostToDevice));
   return SPW_OK;
@@ -415,7 +427,7 @@ void la_plan_free(LaPlan& plan) {
 int la_trace_read(const LaPlan& plan, std::vector<unsigned long long>& out) {
   out.clear();
   if (!plan.d_trace) return SPW_OK;
-  out.resize(3 * (size_t)plan.nblk);
+  out.resize(8 * (size_t)plan.nblk);
   SPW_CUDA(cudaMemcpy(out.data(), plan.d_trace, sizeof(unsigned long long) * out.size(), cudaMemcpyDeviceToHost));
   return SPW_OK;
 }
@@ -471,6 +483,13 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   int* d_done = plan.d_flags;
   int* lls_done = plan.d_flags + 1;
   SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(nblk + 1), st));
+  if (plan.d_trace) {                                        // start stamps are minima, end stamps maxima
+    for (int j = 0; j < nblk; ++j) {
+      SPW_CUDA(cudaMemsetAsync(plan.d_trace + 8 * j, 0, 8 * sizeof(unsigned long long), st));
+      SPW_CUDA(cudaMemsetAsync(plan.d_trace + 8 * j + 3, 0xff, sizeof(unsigned long long), st));
+      SPW_CUDA(cudaMemsetAsync(plan.d_trace + 8 * j + 5, 0xff, sizeof(unsigned long long), st));
+    }
+  }
   // fork: the side and bulk streams join the caller's stream (and its graph capture)
   SPW_CUDA(cudaEventRecord(s.ev_fork, st));
   SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
@@ -482,7 +501,7 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
     const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
     if (nrow > 0) {
       panel2_kernel<4><<<ceil_div(nrow, 32), 128, sizeof(Panel2Smem), s.side>>>(L, j, plan.n, plan.rows, rbeg, dinv, d_done,
-                                                                                 status);
+                                                                                 status, plan.d_trace ? plan.d_trace + 8 * j + 3 : nullptr);
       SPW_LAUNCHED();
     }
     const int m = j / per;
@@ -501,6 +520,7 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
       if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_g[c / per], 0));
       GemmSync done;
       done.done_ctr = lls_done + c;
+      if (plan.d_trace) done.stamp = plan.d_trace + 8 * c + 5;
       SPW_TRY(run(plan.lls[c], s.side, &done));
     }
   }

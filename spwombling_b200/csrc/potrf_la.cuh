@@ -23,7 +23,7 @@ struct LaPlan {
   int n_tasks = 0;
   int* d_flags = nullptr;                       // [0]: diagonal steps published; [1 + c]: CTAs of LLS(c) that have finished
   int* d_expect = nullptr;                      // CTAs per LLS(c) launch
-  unsigned long long* d_trace = nullptr;        // optional (SPW_LA_TRACE=1): per step: wait begins, step begins, step published (ns)
+  unsigned long long* d_trace = nullptr;        // optional (SPW_LA_TRACE=1): 8 words per step (ns): chain wait begins, step begins, step published, PANEL2(j) first start / last end, LLS(j) first start / last end
 };
 
 struct LaStreams {
