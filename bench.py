@@ -420,7 +420,7 @@ def bench_hlm(spw, args):
         out["n%d" % n] = {"iters_per_s": its, "niter": niter, "ms_per_factorisation": dt / niter / 3 * 1e3,
                           "cholesky_tflops": tf, "cholesky_frac": tf / peak_tf,
                           "schedule": ("single persistent CTA" if n <= 200 else
-                                       "shadow schedule (SPW_LA=0)" if os.environ.get("SPW_LA", "")[:1] == "0" or n < 2048
+                                       "shadow schedule (SPW_LA=0)" if os.environ.get("SPW_LA", "")[:1] == "0" or n < 1024
                                        else "look-ahead schedule with a resident diagonal chain (potrf_la.cu)"),
                           "note": "wall clock of spw_hlm_run through the C ABI (H2D/D2H, plan and CUDA-graph set-up "
                                   "included); 3 Cholesky factorisations of order n+1 per iteration ((n+1)^3/3 flop "
