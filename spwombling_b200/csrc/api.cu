@@ -871,11 +871,13 @@ int spw_shutdown(void) {
     }
     c.la_plans.clear();
     if (c.la_streams.side) cudaStreamDestroy(c.la_streams.side);
+    if (c.la_streams.side2) cudaStreamDestroy(c.la_streams.side2);
+    if (c.la_streams.ev_join2) cudaEventDestroy(c.la_streams.ev_join2);
     for (int i = 0; i < LaStreams::NBULK; ++i) {
       if (c.la_streams.bulk[i]) cudaStreamDestroy(c.la_streams.bulk[i]);
       if (c.la_streams.ev_bjoin[i]) cudaEventDestroy(c.la_streams.ev_bjoin[i]);
     }
-    for (auto* v : {&c.la_streams.ev_p, &c.la_streams.ev_g})
+    for (auto* v : {&c.la_streams.ev_p, &c.la_streams.ev_g, &c.la_streams.ev_s})
       for (auto e : *v) cudaEventDestroy(e);
     if (c.la_streams.ev_fork) cudaEventDestroy(c.la_streams.ev_fork);
     if (c.la_streams.ev_join) cudaEventDestroy(c.la_streams.ev_join);

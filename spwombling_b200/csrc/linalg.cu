@@ -70,6 +70,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto issue = [&](int kt) {   // one thread: wait for the slot, arm the barrier, launch the two tile loads
     const int s = kt % Cfg::STAGES;
     mbar_wait(&empty[s], ((kt / Cfg::STAGES) & 1) ^ 1);
+    if (sy.late_flag && kt >= nkt - sy.late_tiles) {
+      const unsigned long long t0 = globaltimer();
+      while (ld_acquire(sy.late_flag) < sy.late_val && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
+      fence_proxy_async();
+    }
     double* st = pipe + (size_t)s * Cfg::STAGE;
     mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
     tma_load_3d(st, &tmA, t.a_col + kt * G_BK, t.a_row, b, &full[s]);

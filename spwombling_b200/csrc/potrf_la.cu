@@ -213,7 +213,7 @@ struct Panel2Smem {
 template <int NW>     // warps per CTA = 8-row groups (4: 32 rows per CTA)
 __global__ void __launch_bounds__(32 * NW, 3)    // <= 168 registers: a CTA fits the slot a 32 x 64 GEMM CTA frees
 panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restrict__ dinv, const int* __restrict__ d_done,
-              int* __restrict__ status, unsigned long long* __restrict__ stamp) {
+              int* __restrict__ status, unsigned long long* __restrict__ stamp, int* __restrict__ p2_done) {
   extern __shared__ __align__(16) unsigned char psm[];
   Panel2Smem& sm = *reinterpret_cast<Panel2Smem*>(psm);
   constexpr int NT = 32 * NW, RB = 8 * NW;
@@ -324,9 +324,15 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
       else if (c < bs) dst[c] = acc[nt][0];
     }
   }
-  if (stamp) {
+  if (stamp || p2_done) {
     __syncthreads();
-    if (tid == 0) atomicMax(stamp + 1, globaltimer());
+    if (tid == 0) {
+      if (p2_done) {                       // the late k-tiles of LLS(j + 2), already running, wait for every CTA of this launch
+        __threadfence();
+        atomicAdd(p2_done, 1);
+      }
+      if (stamp) atomicMax(stamp + 1, globaltimer());
+    }
   }
 }
 
@@ -407,7 +413,7 @@ int la_plan_build(LaPlan& plan, int n, int extra_rows) {
   }
   std::vector<int> expect(nblk, 0);
   for (int c = 0; c < nblk; ++c) expect[c] = plan.lls[c].count;
-  SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(nblk + 1)));
+  SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(2 * nblk + 1)));
   SPW_CUDA(cudaMalloc(&plan.d_expect, sizeof(int) * (size_t)nblk));
   if (env_int("SPW_LA_TRACE", 0)) {
     SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 8 * (size_t)nblk));
@@ -437,8 +443,11 @@ int la_streams_reserve(LaStreams& s, int nblk) {
     int lo = 0, hi = 0;
     SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaStreamCreateWithPriority(&s.side2, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming));
     for (int i = 0; i < LaStreams::NBULK; ++i) {
-      SPW_CUDA(cudaStreamCreateWithPriority(&s.bulk[i], cudaStreamNonBlocking, lo));
+      // bulk[3] carries the nearest target of every outer block: one priority level above the rest where there is one
+      SPW_CUDA(cudaStreamCreateWithPriority(&s.bulk[i], cudaStreamNonBlocking, (i == 3 && lo - hi >= 2) ? lo - 1 : lo));
       SPW_CUDA(cudaEventCreateWithFlags(&s.ev_bjoin[i], cudaEventDisableTiming));
     }
     SPW_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
@@ -452,6 +461,7 @@ int la_streams_reserve(LaStreams& s, int nblk) {
     }
     return SPW_OK;
   };
+  SPW_TRY(grow(s.ev_s, nblk + 1));
   SPW_TRY(grow(s.ev_p, nblk / (OUTER_W / NB) + 2));
   SPW_TRY(grow(s.ev_g, nblk / (OUTER_W / NB) + 2));
   return SPW_OK;
@@ -482,7 +492,14 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   };
   int* d_done = plan.d_flags;
   int* lls_done = plan.d_flags + 1;
-  SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(nblk + 1), st));
+  int* p2_done = plan.d_flags + 1 + nblk;
+  // SPW_LA_EARLY (default 1): LLS(j + 2) is launched one step early, on a second side stream, right after PANEL2(j - 1):
+  // it works through the sources that exist and loads its last two k-tiles (source j) once every CTA of PANEL2(j)
+  // has counted itself in p2_done[j].  The side chain of a step shrinks from PANEL2 + LLS to PANEL2 + two k-tiles.
+  static const bool early = env_int("SPW_LA_EARLY", 1) != 0;
+  static const bool by_distance = env_int("SPW_LA_BULK_BY_DISTANCE", 1) != 0;
+  std::vector<char> touched(plan.nouter + 1, 0);
+  SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(2 * nblk + 1), st));
   if (plan.d_trace) {                                        // start stamps are minima, end stamps maxima
     for (int j = 0; j < nblk; ++j) {
       SPW_CUDA(cudaMemsetAsync(plan.d_trace + 8 * j, 0, 8 * sizeof(unsigned long long), st));
@@ -493,40 +510,72 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   // fork: the side and bulk streams join the caller's stream (and its graph capture)
   SPW_CUDA(cudaEventRecord(s.ev_fork, st));
   SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
+  SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_fork, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) SPW_CUDA(cudaStreamWaitEvent(s.bulk[i], s.ev_fork, 0));
   diag_chain_kernel<<<1, DIAG_THREADS, sizeof(LaSmem), st>>>(L, plan.n, dinv, nblk, status, plan.d_flags, plan.d_expect,
                                                              plan.d_trace);
   SPW_LAUNCHED();
+  // LLS(c) on stream q; late_src >= 0: its last two k-tiles (source late_src = c - 2) wait for PANEL2(late_src)
+  auto launch_lls = [&](int c, cudaStream_t q, int late_src) -> int {
+    GemmSync done;
+    done.done_ctr = lls_done + c;
+    if (plan.d_trace) done.stamp = plan.d_trace + 8 * c + 5;
+    if (late_src >= 0) {
+      const int rb = std::min((late_src + 2) * NB, plan.n);
+      done.late_flag = p2_done + late_src;
+      done.late_val = ceil_div(plan.rows - rb, 32);
+      done.late_tiles = NB / 32;
+    }
+    // the first LLS into outer block cb waits for the last bulk update into it, G(cb - 2, cb)
+    if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[c / per], 0));
+    return run(plan.lls[c], q, &done);
+  };
   for (int j = 0; j < nblk; ++j) {
     const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
     if (nrow > 0) {
       panel2_kernel<4><<<ceil_div(nrow, 32), 128, sizeof(Panel2Smem), s.side>>>(L, j, plan.n, plan.rows, rbeg, dinv, d_done,
-                                                                                 status, plan.d_trace ? plan.d_trace + 8 * j + 3 : nullptr);
+                                                                                 status, plan.d_trace ? plan.d_trace + 8 * j + 3 : nullptr,
+                                                                                 early ? p2_done + j : nullptr);
       SPW_LAUNCHED();
     }
     const int m = j / per;
     if ((j + 1) % per == 0 && !plan.bulk[m].empty()) {       // the panels of outer block m are final
       SPW_CUDA(cudaEventRecord(s.ev_p[m], s.side));
+      // target outer block cb on stream cb mod 3, except the nearest one (awaited two steps from now), which has a
+      // stream of its own and so never queues behind the previous block's updates of far targets; successive
+      // updates of one target are ordered through its event
+      int idx = 0;
       for (const auto& bl : plan.bulk[m]) {
-        cudaStream_t q = s.bulk[bl.cb % LaStreams::NBULK];
+        const bool urgent = by_distance && idx == 0;
+        cudaStream_t q = s.bulk[urgent ? 3 : bl.cb % 3];
         SPW_CUDA(cudaStreamWaitEvent(q, s.ev_p[m], 0));
+        if (urgent && touched[bl.cb]) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[bl.cb], 0));
         SPW_TRY(run(bl.tasks, q, nullptr));
         SPW_CUDA(cudaEventRecord(s.ev_g[bl.cb], q));
+        touched[bl.cb] = 1;
+        ++idx;
       }
     }
-    const int c = j + 2;
-    if (c < nblk) {
-      // the first LLS into outer block cb waits for the last bulk update into it, G(cb - 2, cb)
-      if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_g[c / per], 0));
-      GemmSync done;
-      done.done_ctr = lls_done + c;
-      if (plan.d_trace) done.stamp = plan.d_trace + 8 * c + 5;
-      SPW_TRY(run(plan.lls[c], s.side, &done));
+    if (early) {
+      // PANEL2(j) is launched: LLS(j + 3) may start on the second side stream (its sources up to j exist when
+      // PANEL2(j) has finished: event; source j + 1 comes later, through p2_done[j + 1])
+      SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));
+      const int c = j + 3;
+      if (j == 0) SPW_TRY(launch_lls(2, s.side, -1));                 // LLS(2): one source, nothing to start early on
+      if (c < nblk) {
+        SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_s[j], 0));
+        SPW_TRY(launch_lls(c, s.side2, j + 1));
+      }
+    } else {
+      const int c = j + 2;
+      if (c < nblk) SPW_TRY(launch_lls(c, s.side, -1));
     }
   }
   // join
   SPW_CUDA(cudaEventRecord(s.ev_join, s.side));
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
+  SPW_CUDA(cudaEventRecord(s.ev_join2, s.side2));
+  SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join2, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) {
     SPW_CUDA(cudaEventRecord(s.ev_bjoin[i], s.bulk[i]));
     SPW_CUDA(cudaStreamWaitEvent(st, s.ev_bjoin[i], 0));
