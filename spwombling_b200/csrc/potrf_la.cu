@@ -60,8 +60,10 @@ static_assert(offsetof(DiagSmem, Xt) == sizeof(double) * DIAG_LOW * DIAG_TS, "Lt
 
 // One step of the chain: the look-ahead products of row block j and the sweep of diagonal block j.  sm.xp holds the
 // packed inverse of diagonal block j-1 on entry and that of block j on exit.
+// la_done != nullptr: tile (j, j-1) arrives with source j-2 already applied (U1 kernel, see below), and L(j, j-1) is
+// announced through *la_done = j as soon as it is in global memory (the U1 launch of the next row block waits for it).
 __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, double* __restrict__ dinv, int nblk,
-                                        int* __restrict__ status) {
+                                        int* __restrict__ status, int* __restrict__ la_done) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const MatView none{nullptr, 0, 0};
   const int r0 = j * NB, bs = min(NB, n - r0);
@@ -69,7 +71,7 @@ __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, dou
   double* Lg = L.p;
   if (j > 0) {
     double* T = sm.diag.Lt;
-    const bool two = j >= 2;
+    const bool two = j >= 2 && !la_done;
     const double* a1 = Lg + (long long)r0 * ld + (j - 1) * NB;            // tile (j, j-1)
     const double* b1 = Lg + (long long)(r0 - NB) * ld + (j - 2) * NB;     // L(j-1, j-2)
     const double* x1p = Lg + (long long)r0 * ld + (j - 2) * NB;           // L(j, j-2)
@@ -141,6 +143,10 @@ __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, dou
       chain_panel_rows(T, sm.xp, warp, Lg + (long long)r0 * ld + (j - 1) * NB, ld, bs, NB, lane);
     }
     __syncthreads();
+    if (la_done && tid == DIAG_THREADS - 32) {          // a lane of the last warp: off the pivot warp's scheduler
+      __threadfence();
+      st_release(la_done, j);
+    }
     // ---- tile (j, j) -= L(j, j-1) L(j, j-1)^T: 36 lower 8 x 8 tiles, three per warp; the result feeds the sweep ----
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -169,7 +175,8 @@ __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, dou
 // device or go unnoticed.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __restrict__ status,
-                  int* __restrict__ flags, const int* __restrict__ expect, unsigned long long* __restrict__ trace) {
+                  int* __restrict__ flags, const int* __restrict__ expect, unsigned long long* __restrict__ trace,
+                  int* __restrict__ la_done, const int* __restrict__ u1_done) {
   extern __shared__ __align__(16) unsigned char lsm[];
   LaSmem& sm = *reinterpret_cast<LaSmem*>(lsm);
   const int tid = threadIdx.x;
@@ -179,7 +186,8 @@ diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __
     if (tid == 0 && j >= 2 && !stalled) {
       const int want = expect[j];
       const unsigned long long t0 = globaltimer();
-      while (ld_acquire(flags + 1 + j) < want) {
+      const int want_u = (min(NB, n - j * NB) + 31) / 32;      // CTAs of the U1 launch for row block j
+      while (ld_acquire(flags + 1 + j) < want || (u1_done && ld_acquire(u1_done + j) < want_u)) {
         if (globaltimer() - t0 > 2000000000ull) {
           atomicExch(status, LA_STALLED);
           stalled = true;
@@ -189,7 +197,7 @@ diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __
     }
     __syncthreads();
     if (trace && tid == 0) trace[8 * j + 1] = globaltimer();
-    la_step(sm, L, j, n, dinv, nblk, status);
+    la_step(sm, L, j, n, dinv, nblk, status, la_done);
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -213,7 +221,8 @@ struct Panel2Smem {
 template <int NW>     // warps per CTA = 8-row groups (4: 32 rows per CTA)
 __global__ void __launch_bounds__(32 * NW, 3)    // <= 168 registers: a CTA fits the slot a 32 x 64 GEMM CTA frees
 panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restrict__ dinv, const int* __restrict__ d_done,
-              int* __restrict__ status, unsigned long long* __restrict__ stamp, int* __restrict__ p2_done) {
+              int d_want, int* __restrict__ status, unsigned long long* __restrict__ stamp, int* __restrict__ p2_done,
+              const int* __restrict__ flag2, int want2, int update_only) {
   extern __shared__ __align__(16) unsigned char psm[];
   Panel2Smem& sm = *reinterpret_cast<Panel2Smem*>(psm);
   constexpr int NT = 32 * NW, RB = 8 * NW;
@@ -223,7 +232,7 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
   if (d_done) {
     if (tid == 0) {
       const unsigned long long t0 = globaltimer();
-      while (ld_acquire(d_done) < j + 1) {
+      while (ld_acquire(d_done) < d_want || (flag2 && ld_acquire(flag2) < want2)) {
         if (globaltimer() - t0 > 2000000000ull || ld_relaxed(status) == LA_STALLED) {
           atomicExch(status, LA_STALLED);
           break;
@@ -254,8 +263,9 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
   for (int i = 0; i < PB; ++i) {
     const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
     vb[i] = make_double2(0.0, 0.0);
+    vd[i] = make_double2(0.0, 0.0);
     if (upd && r < bs) vb[i] = __ldcg(reinterpret_cast<const double2*>(b1 + (long long)r * ld + c));
-    vd[i] = __ldcg(reinterpret_cast<const double2*>(dv + r * NB + c));
+    if (!update_only) vd[i] = __ldcg(reinterpret_cast<const double2*>(dv + r * NB + c));
   }
   double x1[16];
 #pragma unroll
@@ -275,7 +285,7 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
     *reinterpret_cast<double2*>(sm.B + r * C_LD + c) = upd ? vb[i] : vd[i];
   }
   __syncthreads();
-  double acc[8][2];
+  double acc[8][2] = {};
   double* crow = sm.T + (8 * warp + g) * C_LD + 2 * q;
   if (upd) {
 #pragma unroll
@@ -290,20 +300,22 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) dmma884(acc[nt][0], acc[nt][1], av, brow[8 * nt * C_LD + 4 * k4]);
     }
+    if (!update_only) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(crow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
-    __syncthreads();                     // every warp is done with L(j, j-1): the buffer takes Dinv(j)
+      for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<double2*>(crow + 8 * nt) = make_double2(acc[nt][0], acc[nt][1]);
+      __syncthreads();                   // every warp is done with L(j, j-1): the buffer takes Dinv(j)
 #pragma unroll
-    for (int i = 0; i < PB; ++i) {
-      const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
-      *reinterpret_cast<double2*>(sm.B + r * C_LD + c) = vd[i];
+      for (int i = 0; i < PB; ++i) {
+        const int e = tid + i * NT, r = e >> 5, c = (e & 31) * 2;
+        *reinterpret_cast<double2*>(sm.B + r * C_LD + c) = vd[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  // rows 8 warp .. 8 warp + 7 times Dinv(j)^T (lower triangular: k <= column)
+  if (!update_only) {
+    // rows 8 warp .. 8 warp + 7 times Dinv(j)^T (lower triangular: k <= column)
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-  {
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
     const double* arow = sm.T + (8 * warp + g) * C_LD + q;
     const double* brow = sm.B + g * C_LD + q;
 #pragma unroll
@@ -314,14 +326,15 @@ panel2_kernel(MatView L, int j, int n, int rows, int rbeg, const double* __restr
         if (nt >= (k4 >> 1)) dmma884(acc[nt][0], acc[nt][1], av, brow[8 * nt * C_LD + 4 * k4]);
     }
   }
+  // update_only: acc holds A(r, j) - L(r, j-1) L(j, j-1)^T, written back in place (the tile the chain kernel picks up)
   const int r = 8 * warp + g;
   if (r < nr) {
     double* dst = L.p + (long long)(r0 + r) * ld + j * NB;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = 8 * nt + 2 * q;
-      if (c + 1 < bs) *reinterpret_cast<double2*>(dst + c) = make_double2(acc[nt][0], acc[nt][1]);
-      else if (c < bs) dst[c] = acc[nt][0];
+      if (c + 1 < bs) __stcg(reinterpret_cast<double2*>(dst + c), make_double2(acc[nt][0], acc[nt][1]));
+      else if (c < bs) __stcg(dst + c, acc[nt][0]);
     }
   }
   if (stamp || p2_done) {
@@ -413,7 +426,7 @@ int la_plan_build(LaPlan& plan, int n, int extra_rows) {
   }
   std::vector<int> expect(nblk, 0);
   for (int c = 0; c < nblk; ++c) expect[c] = plan.lls[c].count;
-  SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(2 * nblk + 1)));
+  SPW_CUDA(cudaMalloc(&plan.d_flags, sizeof(int) * (size_t)(3 * nblk + 2)));
   SPW_CUDA(cudaMalloc(&plan.d_expect, sizeof(int) * (size_t)nblk));
   if (env_int("SPW_LA_TRACE", 0)) {
     SPW_CUDA(cudaMalloc(&plan.d_trace, sizeof(unsigned long long) * 8 * (size_t)nblk));
@@ -444,6 +457,8 @@ int la_streams_reserve(LaStreams& s, int nblk) {
     SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side2, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaStreamCreateWithPriority(&s.side3, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join3, cudaEventDisableTiming));
     SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming));
     for (int i = 0; i < LaStreams::NBULK; ++i) {
       // bulk[3] carries the nearest target of every outer block: one priority level above the rest where there is one
@@ -497,9 +512,15 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   // it works through the sources that exist and loads its last two k-tiles (source j) once every CTA of PANEL2(j)
   // has counted itself in p2_done[j].  The side chain of a step shrinks from PANEL2 + LLS to PANEL2 + two k-tiles.
   static const bool early = env_int("SPW_LA_EARLY", 1) != 0;
+  // SPW_LA_U1 (default 1, needs SPW_LA_EARLY): the first look-ahead product of the chain, tile (j+1, j) -= L(j+1, j-1)
+  // L(j, j-1)^T, is taken off the chain: a two-CTA launch per step on a third side stream does it while the sweep of
+  // block j runs (it waits for la_done >= j, which the chain kernel publishes right after L(j, j-1), and for PANEL2(j-1))
+  static const bool u1 = early && env_int("SPW_LA_U1", 1) != 0;
+  int* la_done = plan.d_flags + 2 * nblk + 1;
+  int* u1_done = plan.d_flags + 2 * nblk + 2;
   static const bool by_distance = env_int("SPW_LA_BULK_BY_DISTANCE", 1) != 0;
   std::vector<char> touched(plan.nouter + 1, 0);
-  SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(2 * nblk + 1), st));
+  SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(3 * nblk + 2), st));
   if (plan.d_trace) {                                        // start stamps are minima, end stamps maxima
     for (int j = 0; j < nblk; ++j) {
       SPW_CUDA(cudaMemsetAsync(plan.d_trace + 8 * j, 0, 8 * sizeof(unsigned long long), st));
@@ -511,10 +532,20 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   SPW_CUDA(cudaEventRecord(s.ev_fork, st));
   SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
   SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_fork, 0));
+  SPW_CUDA(cudaStreamWaitEvent(s.side3, s.ev_fork, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) SPW_CUDA(cudaStreamWaitEvent(s.bulk[i], s.ev_fork, 0));
   diag_chain_kernel<<<1, DIAG_THREADS, sizeof(LaSmem), st>>>(L, plan.n, dinv, nblk, status, plan.d_flags, plan.d_expect,
-                                                             plan.d_trace);
+                                                             plan.d_trace, u1 ? la_done : nullptr, u1 ? u1_done : nullptr);
   SPW_LAUNCHED();
+  auto p2_ctas = [&](int jj) { return std::max(0, ceil_div(plan.rows - std::min((jj + 2) * NB, plan.n), 32)); };
+  if (u1) {
+    for (int j = 1; j + 1 < nblk; ++j) {       // U1(j): source j-1 applied to tile (j+1, j)
+      const int rb0 = (j + 1) * NB, rend = std::min((j + 2) * NB, plan.n);
+      panel2_kernel<4><<<ceil_div(rend - rb0, 32), 128, sizeof(Panel2Smem), s.side3>>>(
+          L, j, plan.n, rend, rb0, dinv, la_done, j, status, nullptr, u1_done + (j + 1), p2_done + (j - 1), p2_ctas(j - 1), 1);
+      SPW_LAUNCHED();
+    }
+  }
   // LLS(c) on stream q; late_src >= 0: its last two k-tiles (source late_src = c - 2) wait for PANEL2(late_src)
   auto launch_lls = [&](int c, cudaStream_t q, int late_src) -> int {
     GemmSync done;
@@ -523,7 +554,7 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
     if (late_src >= 0) {
       const int rb = std::min((late_src + 2) * NB, plan.n);
       done.late_flag = p2_done + late_src;
-      done.late_val = ceil_div(plan.rows - rb, 32);
+      done.late_val = std::max(0, ceil_div(plan.rows - rb, 32));
       done.late_tiles = NB / 32;
     }
     // the first LLS into outer block cb waits for the last bulk update into it, G(cb - 2, cb)
@@ -534,8 +565,8 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
     const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
     if (nrow > 0) {
       panel2_kernel<4><<<ceil_div(nrow, 32), 128, sizeof(Panel2Smem), s.side>>>(L, j, plan.n, plan.rows, rbeg, dinv, d_done,
-                                                                                 status, plan.d_trace ? plan.d_trace + 8 * j + 3 : nullptr,
-                                                                                 early ? p2_done + j : nullptr);
+                                                                                 j + 1, status, plan.d_trace ? plan.d_trace + 8 * j + 3 : nullptr,
+                                                                                 early ? p2_done + j : nullptr, nullptr, 0, 0);
       SPW_LAUNCHED();
     }
     const int m = j / per;
@@ -576,6 +607,8 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
   SPW_CUDA(cudaEventRecord(s.ev_join2, s.side2));
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join2, 0));
+  SPW_CUDA(cudaEventRecord(s.ev_join3, s.side3));
+  SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join3, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) {
     SPW_CUDA(cudaEventRecord(s.ev_bjoin[i], s.bulk[i]));
     SPW_CUDA(cudaStreamWaitEvent(st, s.ev_bjoin[i], 0));
