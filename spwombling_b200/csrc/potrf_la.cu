@@ -370,9 +370,11 @@ int la_plan_build(LaPlan& plan, int n, int extra_rows) {
   plan.n = n;
   plan.rows = n + extra_rows;
   plan.nblk = ceil_div(n, NB);
-  plan.nouter = ceil_div(n, OUTER_W);
+  plan.ow = NB * std::max(1, env_int("SPW_LA_OUTER", OUTER_W / NB));      // columns per outer block of the bulk updates
+  const int OW = plan.ow;
+  plan.nouter = ceil_div(n, OW);
   plan.horizon = std::max(3, env_int("SPW_LA_HORIZON", 1 << 20));
-  const int per = OUTER_W / NB, H = plan.horizon, rows = plan.rows, nblk = plan.nblk;
+  const int per = OW / NB, H = plan.horizon, rows = plan.rows, nblk = plan.nblk;
   std::vector<GemmTask> tasks;
   const int BULK_M = SMALL_M, BULK_N = SMALL_N;
   plan.lls.assign(nblk, ChunkRange{0, 0});
@@ -394,16 +396,16 @@ int la_plan_build(LaPlan& plan, int n, int extra_rows) {
   }
   // bulk updates of outer block cb by the source outer blocks [m0, m1]: lower tiles, column by column
   auto bulk = [&](int m0, int m1, int cb) {
-    const int c_begin = cb * OUTER_W, c_end = std::min(c_begin + OUTER_W, n);
+    const int c_begin = cb * OW, c_end = std::min(c_begin + OW, n);
     for (int c = c_begin; c < c_end; c += BULK_N)
       for (int r = c_begin; r < rows; r += BULK_M) {
         const int m = std::min(BULK_M, rows - r);
         if (c > r + m - 1) continue;
         GemmTask t = la_blank();
-        t.a_row = r; t.a_col = m0 * OUTER_W;
-        t.b_row = c; t.b_col = m0 * OUTER_W;
+        t.a_row = r; t.a_col = m0 * OW;
+        t.b_row = c; t.b_col = m0 * OW;
         t.c_row = r; t.c_col = c;
-        t.m = m; t.n = std::min(BULK_N, n - c); t.k = (m1 - m0 + 1) * OUTER_W;
+        t.m = m; t.n = std::min(BULK_N, n - c); t.k = (m1 - m0 + 1) * OW;
         t.flags = GT_ACCUM | GT_STORE;
         tasks.push_back(t);
       }
@@ -477,13 +479,13 @@ int la_streams_reserve(LaStreams& s, int nblk) {
     return SPW_OK;
   };
   SPW_TRY(grow(s.ev_s, nblk + 1));
-  SPW_TRY(grow(s.ev_p, nblk / (OUTER_W / NB) + 2));
-  SPW_TRY(grow(s.ev_g, nblk / (OUTER_W / NB) + 2));
+  SPW_TRY(grow(s.ev_p, nblk + 2));
+  SPW_TRY(grow(s.ev_g, nblk + 2));
   return SPW_OK;
 }
 
 int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, int* status, cudaStream_t st) {
-  const int nblk = plan.nblk, per = OUTER_W / NB;
+  const int nblk = plan.nblk, per = plan.ow / NB;
   SPW_TRY(la_streams_reserve(s, nblk));
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -561,6 +563,8 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
     if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[c / per], 0));
     return run(plan.lls[c], q, &done);
   };
+  static const int early_rows = env_int("SPW_LA_EARLY_ROWS", 5100);
+  auto is_early = [&](int c) { return early && c >= 3 && plan.rows - c * NB <= early_rows; };
   for (int j = 0; j < nblk; ++j) {
     const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
     if (nrow > 0) {
@@ -587,19 +591,22 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
         ++idx;
       }
     }
-    if (early) {
+    // LLS(j + 2) now, on the side stream -- or it went out a step ago, on the second side stream: early launches pay
+    // when the chain is the bottleneck; while the machine is (a large trailing matrix) their waiting CTAs only take
+    // SM slots from the bulk updates
+    {
+      const int c = j + 2;
+      if (c < nblk && !is_early(c)) SPW_TRY(launch_lls(c, s.side, -1));
+    }
+    {
       // PANEL2(j) is launched: LLS(j + 3) may start on the second side stream (its sources up to j exist when
       // PANEL2(j) has finished: event; source j + 1 comes later, through p2_done[j + 1])
-      SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));
       const int c = j + 3;
-      if (j == 0) SPW_TRY(launch_lls(2, s.side, -1));                 // LLS(2): one source, nothing to start early on
-      if (c < nblk) {
+      if (c < nblk && is_early(c)) {
+        SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));
         SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_s[j], 0));
         SPW_TRY(launch_lls(c, s.side2, j + 1));
       }
-    } else {
-      const int c = j + 2;
-      if (c < nblk) SPW_TRY(launch_lls(c, s.side, -1));
     }
   }
   // join

@@ -14,6 +14,7 @@ constexpr int LA_STALLED = -7;
 
 struct LaPlan {
   int n = 0, rows = 0, nblk = 0, nouter = 0;
+  int ow = OUTER_W;                             // columns per outer block of the bulk updates (SPW_LA_OUTER, in 64-column blocks)
   int horizon = 1 << 20;                        // outer blocks ahead of the chain that receive updates block by block (SPW_LA_HORIZON)
   std::vector<ChunkRange> lls;                  // per TARGET column c: the left-looking product of its recent sources
   struct BulkLaunch { int cb; ChunkRange tasks; };
