@@ -1,43 +1,49 @@
 // Single-matrix blocked Cholesky (order n, NB = 64) with a two-step look-ahead, for the strictly sequential chain of
 // hlmBayes_sp (chol() of R/hlmBayes_sp.R:114,140,181: one matrix of order N + 1 per proposal).
-// DEFAULT from order 1024 on (SPW_LA=0 disables it, SPW_LA_MIN moves the threshold): 4-8 % faster than the shadow
-// schedule of potrf_batched for orders 1000 .. 7000 (2.30-2.36 against 2.45-2.47 ms at 5000; hlmBayes_sp at N = 5000:
-// 136 against 125 iterations/s).
+// DEFAULT from order 1024 on (SPW_LA=0 disables it, SPW_LA_MIN moves the threshold): 7-16 % less time than the shadow
+// schedule of potrf_batched for orders 1000 .. 10000 (2.15 against 2.50 ms at 5001; hlmBayes_sp at N = 5000: 142
+// against 125 iterations/s).
 //
 // The right-looking schedule has the critical path  diag(j) -> panel(j) -> update(j) -> diag(j+1).  Here the chain
 // of diagonal blocks is ONE single-CTA kernel that stays resident for the whole factorisation and finishes its own
 // row block itself, so that step j depends on step j-1 and on work launched TWO steps earlier only:
 //
-//   D(j)      tile (j, j-1) -= L(j, j-2) L(j-1, j-2)^T          (source j-2, the last one missing)
-//             L(j, j-1) = tile (j, j-1) * Dinv(j-1)^T           (panel product of its own row)
+//   D(j)      [tile (j, j-1) -= L(j, j-2) L(j-1, j-2)^T          (source j-2, the last one missing): done by U1(j-1)]
+//             L(j, j-1) = tile (j, j-1) * Dinv(j-1)^T           (panel product of its own row); la_done = j
 //             tile (j, j) -= L(j, j-1) L(j, j-1)^T              (source j-1)
 //             factor and invert tile (j, j)                     (the sweep of diag_factor.cuh)
-//             starts when LLS(j) has finished (a counter its CTAs increment), publishes d_done = j + 1.
+//             starts when LLS(j) and U1(j-1) have finished (counters their CTAs increment), publishes d_done = j + 1.
 //   side stream (highest priority), per step j:
-//     PANEL2(j)  L(r, j) = (A(r, j) - L(r, j-1) L(j, j-1)^T) Dinv(j)^T, rows >= j+2; its CTAs wait for d_done > j
-//     LLS(j+2)   sources s0 .. j -> column j+2, rows >= j+2, ONE product with K = 64 (j + 1 - s0)  (left-looking over
-//                the sources the bulk updates have not covered: s0 = 4 (c / 4 - 1) for target column c)
-//   bulk streams (lowest priority; target outer block cb on stream cb mod 3), when the panels of outer block m
-//   (256 columns) are final, nearest target first:
-//     G(m, cb), cb = m+2 .. m+H-1        K = 256; G(m, m+2) is awaited by the first LLS into block m+2, 3 steps later
-//     LL(0..m -> m+H)                    one product with K = 256 (m+1) when block m+H enters the horizon (SPW_LA_HORIZON;
-//                                        default: no horizon, every update is a G)
+//     PANEL2(j)  L(r, j) = (A(r, j) - L(r, j-1) L(j, j-1)^T) Dinv(j)^T, rows >= j+2; its CTAs wait for d_done > j and
+//                count themselves in p2_done[j]
+//   second side stream:
+//     LLS(c)     sources s0 .. c-2 -> column c, rows >= c, ONE product with K = 64 (c - 1 - s0)  (left-looking over
+//                the sources the bulk updates have not covered: s0 = 4 (c / 4 - 1)).  Launched a step EARLY, after
+//                PANEL2(c-3); its last two k-tiles (source c-2) are loaded once p2_done[c-2] is complete.  (While the
+//                trailing matrix has more than SPW_LA_EARLY_ROWS = 5100 rows: launched after PANEL2(c-2), side stream.)
+//   third side stream:
+//     U1(j)      tile (j+1, j) -= L(j+1, j-1) L(j, j-1)^T (PANEL2's kernel, update only, two CTAs) while the sweep of
+//                block j runs: waits for la_done >= j and p2_done[j-1], counts itself in u1_done[j+1]
+//   bulk streams (lowest priority), when the panels of outer block m (256 columns) are final:
+//     G(m, cb), cb >= m+2      K = 256, target cb on stream cb mod 3, the nearest one (awaited by the first LLS into
+//                              block m+2, two to three steps later) on a stream of its own
+//     (SPW_LA_HORIZON = H: LL(0..m -> m+H), one product with K = 256 (m+1) when block m+H comes near, instead)
 //
-// Every product but PANEL2 is a task list of the TMA-fed DMMA kernel of linalg.cu.  Stream order, three events per
-// outer block and the two flags are the only synchronisation; the pattern forks from and joins the caller's stream,
-// so it can be captured into a CUDA graph.  Deterministic: every tile receives its updates in a fixed order.
+// Every product but PANEL2 / U1 is a task list of the TMA-fed DMMA kernel of linalg.cu.  Stream order, one event per
+// outer block and target, and the flags are the only synchronisation; the pattern forks from and joins the caller's
+// stream, so it is captured into a CUDA graph like any other.  Deterministic: every tile receives its updates in a
+// fixed order.  A flag wait gives up after two seconds (status LA_STALLED).
 //
-// What the per-step trace (SPW_LA_TRACE=1, tools/la_trace.py) shows at order 5001: a chain step takes 20.1 us
-// (1.5 loads + 5.2 look-ahead products at one SM's 250 GFLOP/s + 12.8 sweep + 0.6 hand-over) and the side chain of a
-// step (PANEL2 6.5 us + LLS 12 us) almost as long.  The first ~30 steps are bound by the machine (per-step work >
-// 20 us x 30 TFLOP/s, which is what the trace shows sustained there), the last ~50 by the chain: 32 GFLOP / 30 TFLOP/s
-// + 49 x 20 us = 2.05 ms is the floor of this design; 2.3 ms measured.  The difference sits in outer blocks 5 .. 12:
-// while the ~3000 CTAs of a bulk update wait for SM slots, a kernel launched on the side stream gets its first CTA
-// running 15-27 us late (with a free slot on every SM and with the highest stream priority alike), twice per step.
-// Tried against it, all slower: two bulk CTAs per SM (shared-memory padding), bulk launches of 296 / 441 CTAs that
-// stay resident and walk the task list (the side kernels then start at once, but two bulk CTAs per SM sustain
-// only ~17 TFLOP/s and with three the side CTAs get a quarter of their SM: PANEL2 50 us, LLS 60 us), 128 x 64 bulk
-// tiles, left-looking horizons 3 .. 8, four-stage rings for LLS.  There is no priority inside an SM.
+// What the per-step trace (SPW_LA_TRACE=1, tools/la_trace.py) shows at order 5001: a chain step takes 17.5 us
+// (loads + 3.2 us of look-ahead products at one SM's 250 GFLOP/s + 12.8 us sweep + hand-over), the side chain of a
+// step 12 us.  The first ~30 steps are bound by the machine (~30 TFLOP/s sustained), the last ~50 by the chain.
+// In between (outer blocks 2 .. 12): while the ~3000 CTAs of a bulk update wait for SM slots, a kernel launched on
+// a side stream gets its first CTA running 15-60 us late (with a free slot on every SM and with the highest stream
+// priority alike) and then shares its SM with two bulk CTAs.  Tried against it, all slower: two bulk CTAs per SM
+// (shared-memory padding), bulk launches of 296 / 441 CTAs that stay resident and walk the task list (the side
+// kernels then start at once, but two bulk CTAs per SM sustain only ~17 TFLOP/s and with three the side CTAs get a
+// quarter of their SM: PANEL2 50 us, LLS 60 us), bulk streams by distance, 128 x 64 bulk tiles, outer blocks of
+// 128 .. 512 columns, left-looking horizons 3 .. 8, four-stage rings for LLS.  There is no priority inside an SM.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
