@@ -231,3 +231,19 @@ def test_opt_in_single_matrix_cholesky_schedules_against_oracle(switches, orders
     res = subprocess.run([sys.executable, "-c", _DAG_SCRIPT % {"root": root, "orders": tuple(orders)}], env=env,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-4000:]
+
+
+def test_lookahead_cholesky_repeats_are_bit_identical():
+    """The default single-matrix schedule from order 1024 on couples kernels that run at the same time through flags
+    in global memory: a race there would show as run-to-run differences (tools/la_stress.py is the long version)."""
+    import oracle
+    import spwombling_b200 as spw
+    for n in (1985, 3001):
+        rng = np.random.Generator(np.random.Philox(n))
+        coords = rng.random((n, 2))
+        A = oracle.cov_matern1(oracle.dist_matrix(coords), 8.0, 2.0) + 0.5 * np.eye(n)
+        U0, h0 = spw.chol(A)
+        assert np.linalg.norm(U0.T @ U0 - A) / np.linalg.norm(A) < 1e-13
+        for _ in range(8):
+            U, h = spw.chol(A)
+            assert np.array_equal(U, U0) and h == h0
