@@ -873,6 +873,8 @@ int spw_shutdown(void) {
     if (c.la_streams.side) cudaStreamDestroy(c.la_streams.side);
     if (c.la_streams.side2) cudaStreamDestroy(c.la_streams.side2);
     if (c.la_streams.ev_join2) cudaEventDestroy(c.la_streams.ev_join2);
+    if (c.la_streams.side2b) cudaStreamDestroy(c.la_streams.side2b);
+    if (c.la_streams.ev_join2b) cudaEventDestroy(c.la_streams.ev_join2b);
     if (c.la_streams.side3) cudaStreamDestroy(c.la_streams.side3);
     if (c.la_streams.ev_join3) cudaEventDestroy(c.la_streams.ev_join3);
     for (int i = 0; i < LaStreams::NBULK; ++i) {

@@ -71,8 +71,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int s = kt % Cfg::STAGES;
     mbar_wait(&empty[s], ((kt / Cfg::STAGES) & 1) ^ 1);
     if (sy.late_flag && kt >= nkt - sy.late_tiles) {
+      const int grp = min(1, (kt - (nkt - sy.late_tiles)) / sy.late_group);
       const unsigned long long t0 = globaltimer();
-      while (ld_acquire(sy.late_flag) < sy.late_val && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
+      while (ld_acquire(sy.late_flag + grp) < sy.late_val[grp] && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
       fence_proxy_async();
     }
     double* st = pipe + (size_t)s * Cfg::STAGE;

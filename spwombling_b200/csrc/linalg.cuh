@@ -40,9 +40,10 @@ struct GemmSync {
   const int* wait_flag = nullptr;
   int wait_val = 0;
   int* done_ctr = nullptr;
-  const int* late_flag = nullptr;  // the last late_tiles k-tiles of every task are loaded once *late_flag >= late_val: a
-  int late_val = 0;                // launch may start on the operands that exist and pick up the rest when a kernel
-  int late_tiles = 0;              // that is still running has produced it
+  const int* late_flag = nullptr;  // the last late_tiles k-tiles of every task, in groups of late_group tiles, are loaded once
+  int late_val[2] = {0, 0};        // late_flag[g] >= late_val[g] (g = 0, 1: group): a launch may start on the operands that
+  int late_tiles = 0;              // exist and pick up the rest when kernels that are still running have produced them
+  int late_group = 2;
   unsigned long long* stamp = nullptr;   // optional trace: stamp[0] = earliest CTA start, stamp[1] = latest CTA end (ns)
 };
 // Launches tasks[0 .. count) for every batch entry: C (+)= alpha * A_tile * B_tile^T.  shape: 0 = 128 x 128 tiles

@@ -465,12 +465,14 @@ int la_streams_reserve(LaStreams& s, int nblk) {
     SPW_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side2, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaStreamCreateWithPriority(&s.side2b, cudaStreamNonBlocking, hi));
+    SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join2b, cudaEventDisableTiming));
     SPW_CUDA(cudaStreamCreateWithPriority(&s.side3, cudaStreamNonBlocking, hi));
     SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join3, cudaEventDisableTiming));
     SPW_CUDA(cudaEventCreateWithFlags(&s.ev_join2, cudaEventDisableTiming));
     for (int i = 0; i < LaStreams::NBULK; ++i) {
       // bulk[3] carries the nearest target of every outer block: one priority level above the rest where there is one
-      SPW_CUDA(cudaStreamCreateWithPriority(&s.bulk[i], cudaStreamNonBlocking, (i == 3 && lo - hi >= 2) ? lo - 1 : lo));
+      SPW_CUDA(cudaStreamCreateWithPriority(&s.bulk[i], cudaStreamNonBlocking, (i == 3 && lo - hi >= 2) ? lo - 1 : lo));   // (the priority makes no measurable difference)
       SPW_CUDA(cudaEventCreateWithFlags(&s.ev_bjoin[i], cudaEventDisableTiming));
     }
     SPW_CUDA(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
@@ -540,6 +542,7 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   SPW_CUDA(cudaEventRecord(s.ev_fork, st));
   SPW_CUDA(cudaStreamWaitEvent(s.side, s.ev_fork, 0));
   SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_fork, 0));
+  SPW_CUDA(cudaStreamWaitEvent(s.side2b, s.ev_fork, 0));
   SPW_CUDA(cudaStreamWaitEvent(s.side3, s.ev_fork, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) SPW_CUDA(cudaStreamWaitEvent(s.bulk[i], s.ev_fork, 0));
   diag_chain_kernel<<<1, DIAG_THREADS, sizeof(LaSmem), st>>>(L, plan.n, dinv, nblk, status, plan.d_flags, plan.d_expect,
@@ -559,18 +562,26 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
     GemmSync done;
     done.done_ctr = lls_done + c;
     if (plan.d_trace) done.stamp = plan.d_trace + 8 * c + 5;
-    if (late_src >= 0) {
-      const int rb = std::min((late_src + 2) * NB, plan.n);
+    if (late_src >= 0) {                   // sources late_src .. c - 2 (one or two) come from panels that are still to run
+      const int nlate = c - 1 - late_src;
       done.late_flag = p2_done + late_src;
-      done.late_val = std::max(0, ceil_div(plan.rows - rb, 32));
-      done.late_tiles = NB / 32;
+      for (int g = 0; g < nlate && g < 2; ++g) done.late_val[g] = p2_ctas(late_src + g);
+      done.late_group = NB / 32;
+      done.late_tiles = nlate * (NB / 32);
     }
-    // the first LLS into outer block cb waits for the last bulk update into it, G(cb - 2, cb)
-    if (c % per == 0 && c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[c / per], 0));
+    // an LLS into outer block cb follows the last bulk update into it, G(cb - 2, cb) (every LLS waits, not only the
+    // first one of the block: they are spread over several streams)
+    if (c / per >= 2) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[c / per], 0));
     return run(plan.lls[c], q, &done);
   };
   static const int early_rows = env_int("SPW_LA_EARLY_ROWS", 5100);
-  auto is_early = [&](int c) { return early && c >= 3 && plan.rows - c * NB <= early_rows; };
+  static const int early2_rows = env_int("SPW_LA_EARLY2_ROWS", 3500);
+  auto depth = [&](int c) {
+    if (!early || c < 3) return 0;
+    const int left = plan.rows - c * NB;
+    if (c >= 4 && left <= early2_rows) return 2;
+    return left <= early_rows ? 1 : 0;
+  };
   for (int j = 0; j < nblk; ++j) {
     const int rbeg = std::min((j + 2) * NB, plan.n), nrow = plan.rows - rbeg;
     if (nrow > 0) {
@@ -597,21 +608,23 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
         ++idx;
       }
     }
-    // LLS(j + 2) now, on the side stream -- or it went out a step ago, on the second side stream: early launches pay
-    // when the chain is the bottleneck; while the machine is (a large trailing matrix) their waiting CTAs only take
-    // SM slots from the bulk updates
-    {
-      const int c = j + 2;
-      if (c < nblk && !is_early(c)) SPW_TRY(launch_lls(c, s.side, -1));
-    }
-    {
-      // PANEL2(j) is launched: LLS(j + 3) may start on the second side stream (its sources up to j exist when
-      // PANEL2(j) has finished: event; source j + 1 comes later, through p2_done[j + 1])
-      const int c = j + 3;
-      if (c < nblk && is_early(c)) {
-        SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));
-        SPW_CUDA(cudaStreamWaitEvent(s.side2, s.ev_s[j], 0));
-        SPW_TRY(launch_lls(c, s.side2, j + 1));
+    // LLS(c): depth 0 -- launched now for c = j + 2, on the side stream; depth 1 -- a step early (c = j + 3, second
+    // side stream, last source through p2_done); depth 2 -- two steps early (c = j + 4, alternating between two
+    // streams, last two sources through p2_done).  Early launches pay when the chain is the bottleneck: their launch
+    // latency under load is hidden; while the machine is the bottleneck (a large trailing matrix) their waiting CTAs
+    // only take SM slots from the bulk updates.
+    bool recorded = false;
+    for (int d = 0; d <= 2; ++d) {
+      const int c = j + 2 + d;
+      if (c >= nblk || depth(c) != d) continue;
+      if (d == 0) {
+        SPW_TRY(launch_lls(c, s.side, -1));
+      } else {
+        if (!recorded) SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));    // PANEL2(j) has finished: sources <= j exist
+        recorded = true;
+        cudaStream_t q = (d == 2 && (c & 1)) ? s.side2b : s.side2;
+        SPW_CUDA(cudaStreamWaitEvent(q, s.ev_s[j], 0));
+        SPW_TRY(launch_lls(c, q, j + 1));
       }
     }
   }
@@ -620,6 +633,8 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join, 0));
   SPW_CUDA(cudaEventRecord(s.ev_join2, s.side2));
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join2, 0));
+  SPW_CUDA(cudaEventRecord(s.ev_join2b, s.side2b));
+  SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join2b, 0));
   SPW_CUDA(cudaEventRecord(s.ev_join3, s.side3));
   SPW_CUDA(cudaStreamWaitEvent(st, s.ev_join3, 0));
   for (int i = 0; i < LaStreams::NBULK; ++i) {

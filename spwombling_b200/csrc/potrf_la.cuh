@@ -29,10 +29,10 @@ struct LaPlan {
 
 struct LaStreams {
   static constexpr int NBULK = 4;               // bulk[0..2]: target outer block cb on bulk[cb % 3]; bulk[3]: the nearest target
-  cudaStream_t side = nullptr, side2 = nullptr, side3 = nullptr, bulk[NBULK] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side = nullptr, side2 = nullptr, side2b = nullptr, side3 = nullptr, bulk[NBULK] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> ev_p, ev_g;          // per outer block: its panels are final / the latest bulk update into it
   cudaEvent_t ev_bjoin[NBULK] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join2b = nullptr, ev_join3 = nullptr;
   std::vector<cudaEvent_t> ev_s;                // per step: PANEL2(j) has been launched / finished on the side stream
 };
 
