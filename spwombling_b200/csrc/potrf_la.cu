@@ -529,6 +529,7 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   int* la_done = plan.d_flags + 2 * nblk + 1;
   int* u1_done = plan.d_flags + 2 * nblk + 2;
   static const bool by_distance = env_int("SPW_LA_BULK_BY_DISTANCE", 1) != 0;
+  static const int bulk_delay = by_distance ? env_int("SPW_LA_BULK_DELAY", 1) : 0;
   std::vector<char> touched(plan.nouter + 1, 0);
   SPW_CUDA(cudaMemsetAsync(plan.d_flags, 0, sizeof(int) * (size_t)(3 * nblk + 2), st));
   if (plan.d_trace) {                                        // start stamps are minima, end stamps maxima
@@ -590,38 +591,42 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
                                                                                  early ? p2_done + j : nullptr, nullptr, 0, 0);
       SPW_LAUNCHED();
     }
-    const int m = j / per;
-    if ((j + 1) % per == 0 && !plan.bulk[m].empty()) {       // the panels of outer block m are final
-      SPW_CUDA(cudaEventRecord(s.ev_p[m], s.side));
-      // target outer block cb on stream cb mod 3, except the nearest one (awaited two steps from now), which has a
-      // stream of its own and so never queues behind the previous block's updates of far targets; successive
-      // updates of one target are ordered through its event
+    SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));            // PANEL2(j) has finished: sources <= j exist
+    // bulk updates by outer block m once its panels are final: the nearest target (awaited two to three steps from
+    // now) at once and on a stream of its own, so that it never queues behind the previous block's updates of far
+    // targets; the other targets (stream cb mod 3) one step later (SPW_LA_BULK_DELAY), so that the nearest one has
+    // the machine to itself for a step.  Successive updates of one target are ordered through its event.
+    auto launch_bulk = [&](int m, bool nearest, cudaEvent_t after) -> int {
       int idx = 0;
       for (const auto& bl : plan.bulk[m]) {
         const bool urgent = by_distance && idx == 0;
+        ++idx;
+        if (urgent != nearest) continue;
         cudaStream_t q = s.bulk[urgent ? 3 : bl.cb % 3];
-        SPW_CUDA(cudaStreamWaitEvent(q, s.ev_p[m], 0));
+        SPW_CUDA(cudaStreamWaitEvent(q, after, 0));
         if (urgent && touched[bl.cb]) SPW_CUDA(cudaStreamWaitEvent(q, s.ev_g[bl.cb], 0));
         SPW_TRY(run(bl.tasks, q, nullptr));
         SPW_CUDA(cudaEventRecord(s.ev_g[bl.cb], q));
         touched[bl.cb] = 1;
-        ++idx;
       }
+      return SPW_OK;
+    };
+    if ((j + 1) % per == 0 && !plan.bulk[j / per].empty()) {      // the panels of outer block j / per are final
+      SPW_TRY(launch_bulk(j / per, true, s.ev_s[j]));
+      if (bulk_delay == 0 || j + 1 >= nblk) SPW_TRY(launch_bulk(j / per, false, s.ev_s[j]));
     }
+    if (bulk_delay > 0 && j >= 1 && j % per == 0 && !plan.bulk[j / per - 1].empty()) SPW_TRY(launch_bulk(j / per - 1, false, s.ev_s[j]));
     // LLS(c): depth 0 -- launched now for c = j + 2, on the side stream; depth 1 -- a step early (c = j + 3, second
     // side stream, last source through p2_done); depth 2 -- two steps early (c = j + 4, alternating between two
     // streams, last two sources through p2_done).  Early launches pay when the chain is the bottleneck: their launch
     // latency under load is hidden; while the machine is the bottleneck (a large trailing matrix) their waiting CTAs
     // only take SM slots from the bulk updates.
-    bool recorded = false;
     for (int d = 0; d <= 2; ++d) {
       const int c = j + 2 + d;
       if (c >= nblk || depth(c) != d) continue;
       if (d == 0) {
         SPW_TRY(launch_lls(c, s.side, -1));
       } else {
-        if (!recorded) SPW_CUDA(cudaEventRecord(s.ev_s[j], s.side));    // PANEL2(j) has finished: sources <= j exist
-        recorded = true;
         cudaStream_t q = (d == 2 && (c & 1)) ? s.side2b : s.side2;
         SPW_CUDA(cudaStreamWaitEvent(q, s.ev_s[j], 0));
         SPW_TRY(launch_lls(c, q, j + 1));
