@@ -109,6 +109,7 @@ struct DeviceCtx {
   std::map<std::pair<int, int>, DagPlan*> dag_plans;
   std::map<std::pair<int, int>, LaPlan*> la_plans;
   LaStreams la_streams;        // side / bulk streams and events of the look-ahead Cholesky (potrf_la.cu)
+  cudaGraphExec_t hlm_exec = nullptr;   // iteration graph of the last hlm call (updated in place by the next one)
   void* ws = nullptr;          // grow-only workspace
   size_t ws_bytes = 0;
   void* ws2 = nullptr;         // grow-only scratch of the summary kernels
@@ -886,6 +887,8 @@ int spw_shutdown(void) {
     if (c.la_streams.ev_fork) cudaEventDestroy(c.la_streams.ev_fork);
     if (c.la_streams.ev_join) cudaEventDestroy(c.la_streams.ev_join);
     c.la_streams = LaStreams();
+    if (c.hlm_exec) cudaGraphExecDestroy(c.hlm_exec);
+    c.hlm_exec = nullptr;
     if (c.ws) cudaFree(c.ws);
     c.ws = nullptr;
     c.ws_bytes = 0;
@@ -1104,6 +1107,7 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   SPW_TRY(get_lookahead(*ctx, n, &ws.la));
   SPW_TRY(get_dag_plan(*ctx, n, 1, &ws.dag));
   SPW_TRY(get_la_plan(*ctx, n, 1, &ws.lap, &ws.las));
+  ws.exec_cache = &ctx->hlm_exec;
   int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
                        b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
                        o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);

@@ -472,11 +472,25 @@ int hlm_run_dev(HlmWorkspace& ws, int type, int n, const double* cx, const doubl
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != SPW_OK) return rc;
     if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); return SPW_ERR_CUDA; }
-    SPW_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    if (ws.exec_cache && *ws.exec_cache) {          // same order, type and schedule as the last call: only parameters differ
+      cudaGraphExecUpdateResultInfo upd;
+      const cudaError_t ue = cudaGraphExecUpdate(*ws.exec_cache, graph, &upd);
+      if (ue == cudaSuccess && upd.result == cudaGraphExecUpdateSuccess) {
+        exec = *ws.exec_cache;
+      } else {
+        cudaGetLastError();
+        cudaGraphExecDestroy(*ws.exec_cache);
+        *ws.exec_cache = nullptr;
+      }
+    }
+    if (!exec) {
+      SPW_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      if (ws.exec_cache) *ws.exec_cache = exec;
+    }
     g_launches += per_iter * (long long)(niter - done - 1);   // the captured pass was counted once
     for (; done < niter; ++done) SPW_CUDA(cudaGraphLaunch(exec, st));
     SPW_CUDA(cudaStreamSynchronize(st));
-    cudaGraphExecDestroy(exec);
+    if (!ws.exec_cache) cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
   } else {
     for (; done < niter; ++done) SPW_TRY(iteration());

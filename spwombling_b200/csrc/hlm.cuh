@@ -20,6 +20,8 @@ struct HlmWorkspace {
   const LaPlan* lap = nullptr;        // look-ahead schedule (potrf_la.cu); overrides plan / la
   LaStreams* las = nullptr;
   const DagPlan* dag = nullptr;       // persistent tile-DAG Cholesky (one kernel per factorisation); overrides plan / la
+  cudaGraphExec_t* exec_cache = nullptr;   // optional: the instantiated iteration graph of the previous call on this device,
+                                           // updated in place when the new capture has the same topology (~35 ms less per call)
 };
 
 size_t hlm_state_bytes();

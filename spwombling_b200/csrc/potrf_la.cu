@@ -1,7 +1,7 @@
 // Single-matrix blocked Cholesky (order n, NB = 64) with a two-step look-ahead, for the strictly sequential chain of
 // hlmBayes_sp (chol() of R/hlmBayes_sp.R:114,140,181: one matrix of order N + 1 per proposal).
 // DEFAULT from order 1024 on (SPW_LA=0 disables it, SPW_LA_MIN moves the threshold): 7-16 % less time than the shadow
-// schedule of potrf_batched for orders 1000 .. 10000 (2.15 against 2.50 ms at 5001; hlmBayes_sp at N = 5000: 142
+// schedule of potrf_batched for orders 1000 .. 10000 (2.10 against 2.50 ms at 5001; hlmBayes_sp at N = 5000: 150
 // against 125 iterations/s).
 //
 // The right-looking schedule has the critical path  diag(j) -> panel(j) -> update(j) -> diag(j+1).  Here the chain
