@@ -1107,7 +1107,10 @@ int spw_hlm_run(int n, const double* coords, const double* y, int type, int nite
   SPW_TRY(get_lookahead(*ctx, n, &ws.la));
   SPW_TRY(get_dag_plan(*ctx, n, 1, &ws.dag));
   SPW_TRY(get_la_plan(*ctx, n, 1, &ws.lap, &ws.las));
-  ws.exec_cache = &ctx->hlm_exec;
+  {
+    const char* env = getenv("SPW_HLM_GRAPH_CACHE");     // 0: instantiate the iteration graph anew in every call
+    ws.exec_cache = (env && env[0] == '0') ? nullptr : &ctx->hlm_exec;
+  }
   int rc = hlm_run_dev(ws, type, n, dc.as<double>(), dc.as<double>() + n, dy.as<double>(), niter, report, a_sigma,
                        b_sigma, a_tau, b_tau, lower_phi, upper_phi, dnorm.as<double>(), dunif.as<double>(), want_trgt,
                        o_sig2, o_tau2, o_phi, o_trgt, o_acc, o_tun, info, st);
