@@ -62,7 +62,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_fence_init();
     if (sy.wait_flag) {                       // operands written by a kernel that is still running (see GemmSync)
       const unsigned long long t0 = globaltimer();          // give up after 2 s: never hang the device
-      while (ld_acquire(sy.wait_flag) < sy.wait_val && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
+      while (ld_acquire(sy.wait_flag) < sy.wait_val && globaltimer() - t0 < 2000000000ull &&
+             !(sy.abort_flag && ld_relaxed(sy.abort_flag) == sy.abort_val))
+        __nanosleep(40);
       fence_proxy_async();
     }
   }
@@ -73,7 +75,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (sy.late_flag && kt >= nkt - sy.late_tiles) {
       const int grp = min(1, (kt - (nkt - sy.late_tiles)) / sy.late_group);
       const unsigned long long t0 = globaltimer();
-      while (ld_acquire(sy.late_flag + grp) < sy.late_val[grp] && globaltimer() - t0 < 2000000000ull) __nanosleep(40);
+      while (ld_acquire(sy.late_flag + grp) < sy.late_val[grp] && globaltimer() - t0 < 2000000000ull &&
+             !(sy.abort_flag && ld_relaxed(sy.abort_flag) == sy.abort_val))
+        __nanosleep(40);
       fence_proxy_async();
     }
     double* st = pipe + (size_t)s * Cfg::STAGE;

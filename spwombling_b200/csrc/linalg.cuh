@@ -40,6 +40,8 @@ struct GemmSync {
   const int* wait_flag = nullptr;
   int wait_val = 0;
   int* done_ctr = nullptr;
+  const int* abort_flag = nullptr; // the waits end at once when *abort_flag == abort_val (another kernel has given up)
+  int abort_val = 0;
   const int* late_flag = nullptr;  // the last late_tiles k-tiles of every task, in groups of late_group tiles, are loaded once
   int late_val[2] = {0, 0};        // late_flag[g] >= late_val[g] (g = 0, 1: group): a launch may start on the operands that
   int late_tiles = 0;              // exist and pick up the rest when kernels that are still running have produced them

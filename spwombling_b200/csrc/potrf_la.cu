@@ -562,6 +562,8 @@ int potrf_lookahead(const LaPlan& plan, LaStreams& s, MatView L, double* dinv, i
   auto launch_lls = [&](int c, cudaStream_t q, int late_src) -> int {
     GemmSync done;
     done.done_ctr = lls_done + c;
+    done.abort_flag = status;
+    done.abort_val = LA_STALLED;
     if (plan.d_trace) done.stamp = plan.d_trace + 8 * c + 5;
     if (late_src >= 0) {                   // sources late_src .. c - 2 (one or two) come from panels that are still to run
       const int nlate = c - 1 - late_src;

@@ -247,3 +247,36 @@ def test_lookahead_cholesky_repeats_are_bit_identical():
         for _ in range(8):
             U, h = spw.chol(A)
             assert np.array_equal(U, U0) and h == h0
+
+
+_STALL_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import spwombling_b200 as spw
+from spwombling_b200._lib import SpwError
+import oracle
+n = 1100
+rng = np.random.Generator(np.random.Philox(n))
+coords = rng.random((n, 2))
+A = oracle.cov_matern1(oracle.dist_matrix(coords), 8.0, 2.0) + 0.5 * np.eye(n)
+try:
+    spw.chol(A)
+    print("no error")
+except SpwError as exc:
+    print("error:", exc)
+"""
+
+
+def test_lookahead_cholesky_reports_kernels_that_cannot_run_together():
+    """The look-ahead schedule needs its kernels on the device at the same time.  With CUDA_LAUNCH_BLOCKING=1 every
+    eager launch waits for the previous one to finish: the resident chain kernel gives up its first wait after two
+    seconds and the call must come back with an error that says so -- not hang, not return numbers."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    res = subprocess.run([sys.executable, "-c", _STALL_SCRIPT % {"root": root}], env=env, capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert "did not run at the same time" in res.stdout and "SPW_LA=0" in res.stdout, res.stdout[-2000:]
