@@ -69,7 +69,8 @@ static_assert(offsetof(DiagSmem, Xt) == sizeof(double) * DIAG_LOW * DIAG_TS, "Lt
 // la_done != nullptr: tile (j, j-1) arrives with source j-2 already applied (U1 kernel, see below), and L(j, j-1) is
 // announced through *la_done = j as soon as it is in global memory (the U1 launch of the next row block waits for it).
 __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, double* __restrict__ dinv, int nblk,
-                                        int* __restrict__ status, int* __restrict__ la_done) {
+                                        int* __restrict__ status, int* __restrict__ la_done,
+                                        unsigned long long* __restrict__ tr = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const MatView none{nullptr, 0, 0};
   const int r0 = j * NB, bs = min(NB, n - r0);
@@ -149,10 +150,9 @@ __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, dou
       chain_panel_rows(T, sm.xp, warp, Lg + (long long)r0 * ld + (j - 1) * NB, ld, bs, NB, lane);
     }
     __syncthreads();
-    if (la_done && tid == DIAG_THREADS - 32) {          // a lane of the last warp: off the pivot warp's scheduler
-      __threadfence();
-      st_release(la_done, j);
-    }
+    // st.release.gpu after the CTA barrier publishes the writes of every thread of the CTA (release is cumulative);
+    // no separate fence.sc in front of it
+    if (la_done && tid == DIAG_THREADS - 32) st_release(la_done, j);   // a lane of the last warp: off the pivot warp's scheduler
     // ---- tile (j, j) -= L(j, j-1) L(j, j-1)^T: 36 lower 8 x 8 tiles, three per warp; the result feeds the sweep ----
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -164,6 +164,7 @@ __device__ __forceinline__ void la_step(LaSmem& sm, MatView L, int j, int n, dou
       *reinterpret_cast<double2*>(sm.bufB + (8 * smt[i] + g) * C_LD + 8 * snt[i] + 2 * q) = v;
     }
     __syncthreads();
+    if (tr && tid == 0) tr[7] = globaltimer();           // the sweep starts
     diag_factor_block<false, false, true>(sm.diag, L, 0, j, n, dinv, nblk, none, 0, status, nullptr, sm.bufB);
   } else {
     diag_factor_block<true>(sm.diag, L, 0, j, n, dinv, nblk, none, 0, status, nullptr);
@@ -203,10 +204,9 @@ diag_chain_kernel(MatView L, int n, double* __restrict__ dinv, int nblk, int* __
     }
     __syncthreads();
     if (trace && tid == 0) trace[8 * j + 1] = globaltimer();
-    la_step(sm, L, j, n, dinv, nblk, status, la_done);
+    la_step(sm, L, j, n, dinv, nblk, status, la_done, trace ? trace + 8 * j : nullptr);
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
       st_release(flags, j + 1);
       if (trace) trace[8 * j + 2] = globaltimer();
     }

@@ -22,8 +22,8 @@ wait = t[:, 1] - t[:, 0]
 step = t[:, 2] - t[:, 1]
 print("span %.1f us; steps: sum %.1f us (mean %.2f); waits: sum %.1f us" % (t[-1, 2] - t0, step.sum(), step.mean(), wait.sum()))
 lo, hi = int(os.environ.get("LA_TRACE_FROM", "0")), int(os.environ.get("LA_TRACE_TO", str(nblk)))
-print("  j   t(us)  Dwait Dstep | since D(j-2) published: P2(j-2) start  end | LLS(j) start   end | D(j) starts")
+print("  j   t(us)  Dwait Dstep (look-ahead + sweep) | since D(j-2) published: P2(j-2) start  end | LLS(j) start   end | D(j) starts")
 for j in range(max(2, lo), min(hi, nblk)):
     ref = t[j - 2, 2]
-    print("%3d %7.1f %6.1f %5.1f | %28.1f %5.1f | %12.1f %5.1f | %6.1f" % (
-        j, t[j, 0] - t0, wait[j], step[j], t[j - 2, 3] - ref, t[j - 2, 4] - ref, t[j, 5] - ref, t[j, 6] - ref, t[j, 1] - ref))
+    print("%3d %7.1f %6.1f %5.1f (%4.1f + %4.1f) | %28.1f %5.1f | %12.1f %5.1f | %6.1f" % (
+        j, t[j, 0] - t0, wait[j], step[j], t[j, 7] - t[j, 1], t[j, 2] - t[j, 7], t[j - 2, 3] - ref, t[j - 2, 4] - ref, t[j, 5] - ref, t[j, 6] - ref, t[j, 1] - ref))
