@@ -43,7 +43,8 @@
 // (shared-memory padding), bulk launches of 296 / 441 CTAs that stay resident and walk the task list (the side
 // kernels then start at once, but two bulk CTAs per SM sustain only ~17 TFLOP/s and with three the side CTAs get a
 // quarter of their SM: PANEL2 50 us, LLS 60 us), bulk streams by distance, 128 x 64 bulk tiles, outer blocks of
-// 128 .. 512 columns, left-looking horizons 3 .. 8, four-stage rings for LLS.  There is no priority inside an SM.
+// 128 .. 512 columns, left-looking horizons 3 .. 8, four-stage rings for LLS, the nearest target's update in two
+// halves.  There is no priority inside an SM.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
